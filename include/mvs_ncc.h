@@ -1,0 +1,116 @@
+/*
+ * mvs_ncc.h -- C ABI of the B200 photo-consistency (NCC) scorer.
+ *
+ * This is the drop-in boundary for the one hot path this repo accelerates: the
+ * multi-view-stereo scoring of the reference's MVS2.py.  The reference is pure
+ * Python and has no FFI of its own; each entry point below names the reference
+ * interface (file:line under the reference root) whose work it replaces.  The
+ * Python binding a maintainer adds is a ctypes stub -- see INTEGRATION.md.
+ *
+ * Conventions
+ *   - return value: 0 = MVS_OK, negative = error; mvs_last_error() gives the text
+ *     for the calling thread.  No exceptions cross the ABI.
+ *   - a context owns, on ONE GPU: the gray image stack, the cameras, the cell
+ *     table and scratch buffers.  Callers own every I/O buffer they pass.
+ *   - every I/O pointer of a call is either a host pointer or a device pointer,
+ *     chosen per call by `on_device`.  Host mode copies in, runs, copies out and
+ *     synchronises before returning; device mode only enqueues work on `stream`
+ *     (a cudaStream_t passed as void*; NULL = the legacy default stream).
+ *   - one context per GPU; calls on one context must be serialised by the caller
+ *     (thread-compatible, not thread-safe).
+ *   - there is NO CPU fallback: every entry point fails with MVS_ERR_CUDA when no
+ *     sm_100 device is usable.
+ */
+#ifndef MVS_NCC_H
+#define MVS_NCC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MVS_OK 0
+#define MVS_ERR_ARG (-1)
+#define MVS_ERR_CUDA (-2)
+#define MVS_ERR_NOMEM (-3)
+#define MVS_ERR_STATE (-4)
+
+/* scoring modes for mvs_score_batch */
+#define MVS_MODE_REFEXACT 0 /* "Mode A": literal behaviour of MVS2.py:62-77 */
+#define MVS_MODE_PMVS 1     /* "Mode B": per-view projection, oriented mu x mu bilinear grid */
+
+typedef struct mvs_ctx mvs_ctx;
+
+/* ABI version of this header (checked by the Python loader). */
+int mvs_abi_version(void);
+
+/* Text of the last error raised on the calling thread ("" if none). */
+const char* mvs_last_error(void);
+
+/*
+ * Load the image stack and the cameras into HBM once.
+ * Replaces: main.py:7-20 (read_imgs: list of H x W x 3 uint8 RGB arrays),
+ *           utils.py:56-81 (read_pars: K 3x3, R 3x3, t 3x1 per view),
+ *           HarrisFeatures.py:124-125 (the per-call full-image gray conversion,
+ *           done here once on the device, bit-exact to cv2's BGR2GRAY applied to
+ *           an RGB array), utils.py:242 (cv2.Rodrigues round trip of R).
+ *   rgb  [V,H,W,3] uint8, host or device (rgb_on_device)
+ *   K    [V,9] row-major, only K[0],K[4],K[2],K[5] (fx,fy,cx,cy) enter the path
+ *   R    [V,9] row-major rotation as written in the *_par.txt file
+ *   Rrt  [V,9] the Rodrigues round trip of R computed by the caller (e.g. with
+ *        cv2, which makes projections bit-identical to utils.py:241-244), or NULL
+ *        to let the library compute it (agrees with cv2 to ~1e-14 per entry)
+ *   t    [V,3]
+ */
+int mvs_create(mvs_ctx** out, int device, int V, int H, int W, const uint8_t* rgb, int rgb_on_device,
+               const double* K, const double* R, const double* Rrt, const double* t);
+
+int mvs_destroy(mvs_ctx* ctx);
+
+/* Geometry of the resident stack: views, rows, cols, row pitch in bytes. */
+int mvs_get_info(const mvs_ctx* ctx, int* V, int* H, int* W, int64_t* pitch);
+
+/* Copy the resident gray stack back to the host as a dense [V,H,W] uint8 array. */
+int mvs_download_gray(mvs_ctx* ctx, uint8_t* out_host);
+
+/* Cameras as the device uses them: Rrt [V,9] and centres C = -R^T t [V,3] (file R,
+ * MVS2.py:188-189).  Either pointer may be NULL. */
+int mvs_get_cameras(const mvs_ctx* ctx, double* Rrt_host, double* centres_host);
+
+/*
+ * Score N patch hypotheses.
+ * Replaces: MyPatch.photo_consistenecy_test (MVS2.py:62-77) with ctNcc
+ *           (MVS2.py:39-43), getDescFeatures (HarrisFeatures.py:116-133) and
+ *           projectPoint (utils.py:241-244), for a whole batch.
+ *   mode      MVS_MODE_REFEXACT | MVS_MODE_PMVS
+ *   c   [N,3] patch centres (patch.c)
+ *   nrm [N,3] patch normals (patch.n); unused (may be NULL) in MVS_MODE_REFEXACT,
+ *             exactly as the reference never reads it
+ *   ref [N]   reference view index (patch.R)
+ *   min_ncc   MIN_NCC (0.4 at MVS2.py:255, 0.7 at MVS2.py:362); strict '>'
+ *   wid       half window (reference: hard-coded 5); window = (2*wid+1)^2 pixels.
+ *             In MVS_MODE_PMVS the grid is mu x mu with mu = 2*wid+1.
+ * outputs (any may be NULL except vis_mask and count)
+ *   vis_mask [N, ceil(V/64)] uint64, bit v set <=> view v would be appended to
+ *             patch.V (MVS2.py:72-74)
+ *   avg  [N]  patch.avg_ncc_score (MVS2.py:73,75-76): mean NCC over visible views, 0 if none
+ *   count [N] patch.visible_ct()
+ *   xy  [N,2] the unrounded reference-view projection (x = column, y = row) stored
+ *             in every patch.V entry (MVS2.py:74)
+ *   ncc [N,V] float32, every per-view NCC (NaN where the reference computes none
+ *             or NaN: reference view itself, zero-variance window, out of bounds);
+ *             for parity tests, NULL on the hot path
+ */
+int mvs_score_batch(mvs_ctx* ctx, int mode, int64_t N, const double* c, const double* nrm, const int32_t* ref,
+                    double min_ncc, int wid, uint64_t* vis_mask, double* avg, int32_t* count, double* xy, float* ncc,
+                    int on_device, void* stream);
+
+/* Number of kernels this library has launched on ctx since creation (for bench.py's
+ * gpu_launches claim). */
+int64_t mvs_launch_count(const mvs_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVS_NCC_H */

@@ -332,12 +332,17 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true")
     ap.add_argument("--full-n", type=int, default=1024)
+    ap.add_argument("--only-full", action="store_true", help="leave the committed fixtures untouched")
     a = ap.parse_args()
     if not os.path.isdir(REF):
         raise SystemExit("reference not mounted at /root/reference: golden vectors can only be made in the build container")
     os.makedirs(GOLD, exist_ok=True)
     ref_mvs2, ref_main = import_reference()
     imgs, par_text = load_dino(ref_main)
+    if a.only_full:
+        make_full(ref_mvs2, imgs, par_text, a.full_n)
+        print("oracle/_ref/dinoRing_full.npz done")
+        return
     sub, Ks, Rs, ts, c, ref, scores = make_dino12(ref_mvs2, imgs, par_text)
     print("dino12_scores: N=%d, in-bounds=%d, mean visible(0.4)=%.2f" % (
         len(c), np.isfinite(scores["t04_ncc"]).any(1).sum(), scores["t04_vis"].sum(1).mean()))

@@ -1,0 +1,45 @@
+"""ctypes binding of include/mvs_ncc.h.  Fails loudly when the library is missing:
+there is no CPU or PyTorch fallback for any entry point."""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmvsncc.so")
+ABI_VERSION = 1
+
+# every symbol include/mvs_ncc.h declares: name -> (restype, argtypes)
+_P = C.c_void_p
+SYMBOLS = {
+    "mvs_abi_version": (C.c_int, []),
+    "mvs_last_error": (C.c_char_p, []),
+    "mvs_create": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, _P, _P, _P]),
+    "mvs_destroy": (C.c_int, [_P]),
+    "mvs_get_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int64)]),
+    "mvs_download_gray": (C.c_int, [_P, _P]),
+    "mvs_get_cameras": (C.c_int, [_P, _P, _P]),
+    "mvs_score_batch": (C.c_int, [_P, C.c_int, C.c_int64, _P, _P, _P, C.c_double, C.c_int, _P, _P, _P, _P, _P,
+                                  C.c_int, _P]),
+    "mvs_launch_count": (C.c_int64, [_P]),
+}
+
+_lib = None
+
+
+def load():
+    """dlopen libmvsncc.so and bind every declared symbol (no compute is run)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python __graft_entry__.py` (nvcc, sm_100a). "
+            "There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)          # AttributeError if the .so lacks a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    if lib.mvs_abi_version() != ABI_VERSION:
+        raise ImportError(f"libmvsncc.so has ABI {lib.mvs_abi_version()}, binding expects {ABI_VERSION}: rebuild")
+    _lib = lib
+    return lib

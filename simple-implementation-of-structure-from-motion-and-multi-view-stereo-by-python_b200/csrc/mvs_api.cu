@@ -1,0 +1,308 @@
+// C-ABI entry points (include/mvs_ncc.h): context lifetime, camera preparation,
+// host/device buffer handling.  Kernels live in the other .cu files.
+#include <math.h>
+#include <stdarg.h>
+#include <stdlib.h>
+
+#include "mvs_common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void mvs_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* mvs_last_error(void) { return g_err; }
+extern "C" int mvs_abi_version(void) { return MVS_ABI_VERSION; }
+
+// ---------------------------------------------------------------------------------
+// Rodrigues round trip R' = Rodrigues(Rodrigues(R)) (utils.py:242-243), restated from
+// OpenCV's published algorithm: orthonormalise (OpenCV: U*Vt of the SVD; here the
+// same polar factor by Newton iteration X <- (X + X^-T)/2), take the axis-angle
+// vector, rebuild the matrix.  Host code, fp64, runs once per view at load time.
+// ---------------------------------------------------------------------------------
+static void inv_transpose3(const double* a, double* o) {
+    const double c00 = a[4] * a[8] - a[5] * a[7], c01 = a[5] * a[6] - a[3] * a[8], c02 = a[3] * a[7] - a[4] * a[6];
+    const double c10 = a[2] * a[7] - a[1] * a[8], c11 = a[0] * a[8] - a[2] * a[6], c12 = a[1] * a[6] - a[0] * a[7];
+    const double c20 = a[1] * a[5] - a[2] * a[4], c21 = a[2] * a[3] - a[0] * a[5], c22 = a[0] * a[4] - a[1] * a[3];
+    const double det = a[0] * c00 + a[1] * c01 + a[2] * c02;
+    const double id = 1.0 / det;
+    // inverse = adj/det with adj = cof^T, so inverse-transpose = cof/det
+    o[0] = c00 * id; o[1] = c01 * id; o[2] = c02 * id;
+    o[3] = c10 * id; o[4] = c11 * id; o[5] = c12 * id;
+    o[6] = c20 * id; o[7] = c21 * id; o[8] = c22 * id;
+}
+
+static void rodrigues_roundtrip(const double* Rin, double* out) {
+    double Q[9], T[9];
+    memcpy(Q, Rin, sizeof(Q));
+    for (int it = 0; it < 12; ++it) {
+        inv_transpose3(Q, T);
+        double delta = 0.0;
+        for (int i = 0; i < 9; ++i) {
+            const double nv = 0.5 * (Q[i] + T[i]);
+            delta = fmax(delta, fabs(nv - Q[i]));
+            Q[i] = nv;
+        }
+        if (delta < 1e-17) break;
+    }
+    double rx = Q[7] - Q[5], ry = Q[2] - Q[6], rz = Q[3] - Q[1];
+    const double s = sqrt((rx * rx + ry * ry + rz * rz) * 0.25);
+    double c = (Q[0] + Q[4] + Q[8] - 1.0) * 0.5;
+    c = c > 1.0 ? 1.0 : (c < -1.0 ? -1.0 : c);
+    const double theta = acos(c);
+    double v[3];
+    if (s < 1e-5) {
+        if (c > 0) {
+            v[0] = v[1] = v[2] = 0.0;
+        } else {
+            double tx = sqrt(fmax((Q[0] + 1) * 0.5, 0.0));
+            double ty = sqrt(fmax((Q[4] + 1) * 0.5, 0.0)) * (Q[1] < 0 ? -1.0 : 1.0);
+            double tz = sqrt(fmax((Q[8] + 1) * 0.5, 0.0)) * (Q[2] < 0 ? -1.0 : 1.0);
+            if (fabs(tx) < fabs(ty) && fabs(tx) < fabs(tz) && ((Q[5] > 0) != (ty * tz > 0))) tz = -tz;
+            const double k = theta / sqrt(tx * tx + ty * ty + tz * tz);
+            v[0] = tx * k; v[1] = ty * k; v[2] = tz * k;
+        }
+    } else {
+        const double k = theta / (2.0 * s);
+        v[0] = rx * k; v[1] = ry * k; v[2] = rz * k;
+    }
+    const double th = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    if (th < 2.220446049250313e-16) {
+        const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        memcpy(out, I, sizeof(I));
+        return;
+    }
+    const double kx = v[0] / th, ky = v[1] / th, kz = v[2] / th;
+    const double ct = cos(th), st = sin(th), c1 = 1.0 - ct;
+    out[0] = ct + c1 * kx * kx;      out[1] = c1 * kx * ky - st * kz; out[2] = c1 * kx * kz + st * ky;
+    out[3] = c1 * kx * ky + st * kz; out[4] = ct + c1 * ky * ky;      out[5] = c1 * ky * kz - st * kx;
+    out[6] = c1 * kx * kz - st * ky; out[7] = c1 * ky * kz + st * kx; out[8] = ct + c1 * kz * kz;
+}
+
+static int ensure_stage(mvs_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->stage_bytes) return MVS_OK;
+    if (ctx->d_stage) cudaFree(ctx->d_stage);
+    ctx->d_stage = nullptr;
+    ctx->stage_bytes = 0;
+    size_t want = bytes + bytes / 4 + 4096;
+    if (cudaMalloc(&ctx->d_stage, want) != cudaSuccess) {
+        cudaGetLastError();
+        mvs_set_error("cudaMalloc of %zu staging bytes failed", want);
+        return MVS_ERR_NOMEM;
+    }
+    ctx->stage_bytes = want;
+    return MVS_OK;
+}
+
+extern "C" int mvs_create(mvs_ctx** out, int device, int V, int H, int W, const uint8_t* rgb, int rgb_on_device,
+                          const double* K, const double* R, const double* Rrt, const double* t) {
+    if (!out || !rgb || !K || !R || !t || V < 1 || V > 1024 || H < 1 || W < 1) {
+        mvs_set_error("mvs_create: bad argument (need 1 <= V <= 1024, H, W >= 1, non-null rgb/K/R/t)");
+        return MVS_ERR_ARG;
+    }
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        mvs_set_error("mvs_create: no CUDA device is usable; this library has no CPU fallback");
+        return MVS_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) {
+        mvs_set_error("mvs_create: device %d out of range (0..%d)", device, ndev - 1);
+        return MVS_ERR_ARG;
+    }
+    MVS_CUDA_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    MVS_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        mvs_set_error("mvs_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major,
+                      prop.minor);
+        return MVS_ERR_CUDA;
+    }
+    mvs_ctx* ctx = (mvs_ctx*)calloc(1, sizeof(mvs_ctx));
+    if (!ctx) return MVS_ERR_NOMEM;
+    ctx->device = device;
+    ctx->V = V;
+    ctx->H = H;
+    ctx->W = W;
+    ctx->pitch = ((int64_t)W + 127) / 128 * 128;
+    ctx->vstride = ctx->pitch * H;
+    ctx->sm_count = prop.multiProcessorCount;
+    int rc = MVS_OK;
+    const size_t gray_bytes = (size_t)ctx->vstride * V + 256;
+    const size_t rgb_bytes = (size_t)V * H * W * 3;
+    uint8_t* d_rgb = nullptr;
+    CamProj* hp = (CamProj*)malloc(sizeof(CamProj) * V);
+    CamGeom* hg = (CamGeom*)malloc(sizeof(CamGeom) * V);
+    ctx->h_rrt = (double*)malloc(sizeof(double) * 9 * V);
+    ctx->h_centres = (double*)malloc(sizeof(double) * 3 * V);
+    if (!hp || !hg || !ctx->h_rrt || !ctx->h_centres) {
+        rc = MVS_ERR_NOMEM;
+        goto fail;
+    }
+    for (int v = 0; v < V; ++v) {
+        const double* Rf = R + 9 * v;
+        double* rr = ctx->h_rrt + 9 * v;
+        if (Rrt)
+            memcpy(rr, Rrt + 9 * v, sizeof(double) * 9);
+        else
+            rodrigues_roundtrip(Rf, rr);
+        memcpy(hp[v].r, rr, sizeof(double) * 9);
+        memcpy(hg[v].rf, Rf, sizeof(double) * 9);
+        for (int i = 0; i < 3; ++i) hp[v].t[i] = t[3 * v + i];
+        hp[v].fx = hg[v].fx = K[9 * v + 0];
+        hp[v].fy = hg[v].fy = K[9 * v + 4];
+        hp[v].cx = hg[v].cx = K[9 * v + 2];
+        hp[v].cy = hg[v].cy = K[9 * v + 5];
+        // C = -(R^T t) with the FILE rotation (MVS2.py:188-189), left-to-right sums
+        for (int i = 0; i < 3; ++i) {
+            const double s = Rf[0 * 3 + i] * t[3 * v + 0] + Rf[1 * 3 + i] * t[3 * v + 1] + Rf[2 * 3 + i] * t[3 * v + 2];
+            hg[v].C[i] = ctx->h_centres[3 * v + i] = -s;
+        }
+    }
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMalloc(&ctx->d_gray, gray_bytes) != cudaSuccess || cudaMalloc(&ctx->d_cam, sizeof(CamProj) * V) != cudaSuccess ||
+        cudaMalloc(&ctx->d_geom, sizeof(CamGeom) * V) != cudaSuccess) {
+        mvs_set_error("mvs_create: device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        rc = MVS_ERR_NOMEM;
+        goto fail;
+    }
+    if (cudaMemsetAsync(ctx->d_gray, 0, gray_bytes, ctx->own_stream) != cudaSuccess ||
+        cudaMemcpyAsync(ctx->d_cam, hp, sizeof(CamProj) * V, cudaMemcpyHostToDevice, ctx->own_stream) != cudaSuccess ||
+        cudaMemcpyAsync(ctx->d_geom, hg, sizeof(CamGeom) * V, cudaMemcpyHostToDevice, ctx->own_stream) != cudaSuccess) {
+        mvs_set_error("mvs_create: camera upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+        rc = MVS_ERR_CUDA;
+        goto fail;
+    }
+    if (rgb_on_device) {
+        // the caller's stream ordering is unknown: make its writes visible first
+        if (cudaDeviceSynchronize() != cudaSuccess) { rc = MVS_ERR_CUDA; goto fail; }
+        rc = mvs_launch_gray(ctx, rgb, ctx->own_stream);
+    } else {
+        if (cudaMalloc(&d_rgb, rgb_bytes) != cudaSuccess) {
+            mvs_set_error("mvs_create: cudaMalloc of %zu RGB bytes failed", rgb_bytes);
+            cudaGetLastError();
+            rc = MVS_ERR_NOMEM;
+            goto fail;
+        }
+        if (cudaMemcpyAsync(d_rgb, rgb, rgb_bytes, cudaMemcpyHostToDevice, ctx->own_stream) != cudaSuccess) {
+            mvs_set_error("mvs_create: RGB upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = MVS_ERR_CUDA;
+            goto fail;
+        }
+        rc = mvs_launch_gray(ctx, d_rgb, ctx->own_stream);
+    }
+    if (rc != MVS_OK) goto fail;
+    if (cudaStreamSynchronize(ctx->own_stream) != cudaSuccess) {
+        mvs_set_error("mvs_create: gray conversion failed: %s", cudaGetErrorString(cudaGetLastError()));
+        rc = MVS_ERR_CUDA;
+        goto fail;
+    }
+    if (d_rgb) cudaFree(d_rgb);
+    free(hp);
+    free(hg);
+    *out = ctx;
+    return MVS_OK;
+fail:
+    if (d_rgb) cudaFree(d_rgb);
+    free(hp);
+    free(hg);
+    mvs_destroy(ctx);
+    return rc;
+}
+
+extern "C" int mvs_destroy(mvs_ctx* ctx) {
+    if (!ctx) return MVS_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->d_gray) cudaFree(ctx->d_gray);
+    if (ctx->d_cam) cudaFree(ctx->d_cam);
+    if (ctx->d_geom) cudaFree(ctx->d_geom);
+    if (ctx->d_stage) cudaFree(ctx->d_stage);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    free(ctx->h_rrt);
+    free(ctx->h_centres);
+    free(ctx);
+    return MVS_OK;
+}
+
+extern "C" int mvs_get_info(const mvs_ctx* ctx, int* V, int* H, int* W, int64_t* pitch) {
+    if (!ctx) { mvs_set_error("null context"); return MVS_ERR_ARG; }
+    if (V) *V = ctx->V;
+    if (H) *H = ctx->H;
+    if (W) *W = ctx->W;
+    if (pitch) *pitch = ctx->pitch;
+    return MVS_OK;
+}
+
+extern "C" int mvs_download_gray(mvs_ctx* ctx, uint8_t* out_host) {
+    if (!ctx || !out_host) { mvs_set_error("mvs_download_gray: null argument"); return MVS_ERR_ARG; }
+    MVS_CUDA_CHECK(cudaSetDevice(ctx->device));
+    MVS_CUDA_CHECK(cudaMemcpy2D(out_host, ctx->W, ctx->d_gray, ctx->pitch, ctx->W, (size_t)ctx->V * ctx->H,
+                                cudaMemcpyDeviceToHost));
+    return MVS_OK;
+}
+
+extern "C" int mvs_get_cameras(const mvs_ctx* ctx, double* Rrt_host, double* centres_host) {
+    if (!ctx) { mvs_set_error("null context"); return MVS_ERR_ARG; }
+    if (Rrt_host) memcpy(Rrt_host, ctx->h_rrt, sizeof(double) * 9 * ctx->V);
+    if (centres_host) memcpy(centres_host, ctx->h_centres, sizeof(double) * 3 * ctx->V);
+    return MVS_OK;
+}
+
+extern "C" int64_t mvs_launch_count(const mvs_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+extern "C" int mvs_score_batch(mvs_ctx* ctx, int mode, int64_t N, const double* c, const double* nrm, const int32_t* ref,
+                               double min_ncc, int wid, uint64_t* vis_mask, double* avg, int32_t* count, double* xy,
+                               float* ncc, int on_device, void* stream) {
+    if (!ctx) { mvs_set_error("mvs_score_batch: null context"); return MVS_ERR_ARG; }
+    if (N < 0 || (N > 0 && (!c || !ref || !vis_mask || !count))) {
+        mvs_set_error("mvs_score_batch: c, ref, vis_mask and count are required");
+        return MVS_ERR_ARG;
+    }
+    if (mode != MVS_MODE_REFEXACT) {
+        mvs_set_error("mvs_score_batch: mode %d is not available in this build", mode);
+        return MVS_ERR_ARG;
+    }
+    if (wid < 1 || wid > 7) { mvs_set_error("mvs_score_batch: wid must be in 1..7 (got %d)", wid); return MVS_ERR_ARG; }
+    (void)nrm;
+    if (N == 0) return MVS_OK;
+    MVS_CUDA_CHECK(cudaSetDevice(ctx->device));
+    const int V = ctx->V;
+    const size_t mw = (size_t)((V + 63) / 64);
+    if (on_device) {
+        return mvs_launch_score_refexact(ctx, N, c, ref, min_ncc, wid, vis_mask, avg, count, xy, ncc, (cudaStream_t)stream);
+    }
+    // host mode: stage in, run, stage out, synchronise
+    const size_t b_c = align256(sizeof(double) * 3 * N), b_ref = align256(sizeof(int32_t) * N);
+    const size_t b_vis = align256(sizeof(uint64_t) * mw * N), b_avg = align256(sizeof(double) * N);
+    const size_t b_cnt = align256(sizeof(int32_t) * N), b_xy = align256(sizeof(double) * 2 * N);
+    const size_t b_ncc = ncc ? align256(sizeof(float) * (size_t)V * N) : 0;
+    int rc = ensure_stage(ctx, b_c + b_ref + b_vis + b_avg + b_cnt + b_xy + b_ncc);
+    if (rc != MVS_OK) return rc;
+    cudaStream_t s = ctx->own_stream;
+    uint8_t* p = (uint8_t*)ctx->d_stage;
+    double* d_c = (double*)p; p += b_c;
+    int32_t* d_ref = (int32_t*)p; p += b_ref;
+    uint64_t* d_vis = (uint64_t*)p; p += b_vis;
+    double* d_avg = (double*)p; p += b_avg;
+    int32_t* d_cnt = (int32_t*)p; p += b_cnt;
+    double* d_xy = (double*)p; p += b_xy;
+    float* d_ncc = ncc ? (float*)p : nullptr;
+    MVS_CUDA_CHECK(cudaMemcpyAsync(d_c, c, sizeof(double) * 3 * N, cudaMemcpyHostToDevice, s));
+    MVS_CUDA_CHECK(cudaMemcpyAsync(d_ref, ref, sizeof(int32_t) * N, cudaMemcpyHostToDevice, s));
+    rc = mvs_launch_score_refexact(ctx, N, d_c, d_ref, min_ncc, wid, d_vis, d_avg, d_cnt, d_xy, d_ncc, s);
+    if (rc != MVS_OK) return rc;
+    MVS_CUDA_CHECK(cudaMemcpyAsync(vis_mask, d_vis, sizeof(uint64_t) * mw * N, cudaMemcpyDeviceToHost, s));
+    MVS_CUDA_CHECK(cudaMemcpyAsync(count, d_cnt, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, s));
+    if (avg) MVS_CUDA_CHECK(cudaMemcpyAsync(avg, d_avg, sizeof(double) * N, cudaMemcpyDeviceToHost, s));
+    if (xy) MVS_CUDA_CHECK(cudaMemcpyAsync(xy, d_xy, sizeof(double) * 2 * N, cudaMemcpyDeviceToHost, s));
+    if (ncc) MVS_CUDA_CHECK(cudaMemcpyAsync(ncc, d_ncc, sizeof(float) * (size_t)V * N, cudaMemcpyDeviceToHost, s));
+    MVS_CUDA_CHECK(cudaStreamSynchronize(s));
+    return MVS_OK;
+}

@@ -1,0 +1,61 @@
+// Shared definitions of the B200 NCC scorer library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "mvs_ncc.h"
+
+#define MVS_ABI_VERSION 1
+
+// One view's projection parameters as the scorer reads them (128 B, fp64).
+// r = Rodrigues round trip of the file rotation (utils.py:242-243).
+struct __align__(16) CamProj {
+    double r[9];
+    double t[3];
+    double fx, fy, cx, cy;
+};
+
+// Expansion-side geometry of one view (MVS2.py:188-189, 334-358): FILE rotation and
+// centre C = -R^T t.
+struct __align__(16) CamGeom {
+    double rf[9];
+    double C[3];
+    double fx, fy, cx, cy;
+};
+
+struct mvs_ctx {
+    int device;
+    int V, H, W;
+    int64_t pitch;        // bytes per gray row (multiple of 128)
+    int64_t vstride;      // bytes per gray view = H * pitch
+    uint8_t* d_gray;      // [V, H, pitch] + 256 B tail pad
+    CamProj* d_cam;       // [V]
+    CamGeom* d_geom;      // [V]
+    double* h_rrt;        // [V,9] host copy
+    double* h_centres;    // [V,3]
+    int sm_count;
+    int64_t launches;
+    // host-mode staging (grown on demand)
+    void* d_stage;
+    size_t stage_bytes;
+    cudaStream_t own_stream;
+};
+
+void mvs_set_error(const char* fmt, ...);
+
+#define MVS_CUDA_CHECK(expr)                                                               \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess) {                                                           \
+            mvs_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                          __LINE__);                                                       \
+            return MVS_ERR_CUDA;                                                           \
+        }                                                                                  \
+    } while (0)
+
+// kernels / launchers implemented in the .cu files
+int mvs_launch_gray(mvs_ctx* ctx, const uint8_t* d_rgb, cudaStream_t s);
+int mvs_launch_score_refexact(mvs_ctx* ctx, int64_t N, const double* c, const int32_t* ref, double thr, int wid,
+                              uint64_t* vis, double* avg, int32_t* count, double* xy, float* ncc, cudaStream_t s);

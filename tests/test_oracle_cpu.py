@@ -1,0 +1,112 @@
+"""The oracle (NumPy restatement) against the golden vectors produced by the
+reference itself (oracle/make_golden.py) and against known-answer cases."""
+import numpy as np
+import pytest
+
+from oracle import expansion, mode_a
+from oracle.cameras import Cameras, rodrigues_roundtrip
+
+
+def _cams(d):
+    cams = Cameras(d["K"], d["R"], d["t"])
+    cams.R = d["Rrt"].copy()          # cv2's own round trip, as the reference uses
+    return cams
+
+
+@pytest.mark.parametrize("name", ["dino12_scores", "synth5_scores"])
+@pytest.mark.parametrize("tag,thr", [("t04", 0.4), ("t07", 0.7)])
+def test_mode_a_matches_reference(golden, name, tag, thr):
+    d = golden(name)
+    o = mode_a.score(mode_a.gray_from_rgb(d["rgb"]), _cams(d), d["c"], d["ref"], thr)
+    assert (o["vis"] == d[tag + "_vis"]).all()                       # accepted sets: exact
+    assert (np.isnan(o["ncc"]) == np.isnan(d[tag + "_ncc"])).all()   # NaN / not-scored pattern: exact
+    assert np.nanmax(np.abs(o["ncc"] - d[tag + "_ncc"])) < 1e-12
+    assert np.abs(o["avg"] - d[tag + "_avg"]).max() < 1e-12
+    seen = ~np.isnan(d[tag + "_xy"][:, 0])
+    assert (o["x"][seen] == d[tag + "_xy"][seen, 0]).all()           # projection: bit-exact vs cv2
+    assert (o["y"][seen] == d[tag + "_xy"][seen, 1]).all()
+
+
+def test_literal_walk_matches_closed_form(golden):
+    d = golden("synth5_scores")
+    cams = _cams(d)
+    gray = mode_a.gray_from_rgb(d["rgb"])
+    o = mode_a.score(gray, cams, d["c"], d["ref"], 0.4)
+    for i in range(0, len(d["c"]), 7):
+        out, avg = mode_a.score_literal(list(d["rgb"]), cams, d["c"][i], int(d["ref"][i]), 0.4)
+        assert [v for v, _, _ in out] == list(np.nonzero(o["vis"][i])[0])
+        assert abs(avg - o["avg"][i]) < 1e-12
+
+
+def test_gray_formula_against_cv2():
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 256, (97, 131, 3), dtype=np.uint8)
+    assert (cv2.cvtColor(img.copy(), cv2.COLOR_BGR2GRAY) == mode_a.gray_from_rgb(img)).all()
+    # every value of each channel alone and the extremes
+    ramp = np.zeros((3, 256, 3), np.uint8)
+    for ch in range(3):
+        ramp[ch, :, ch] = np.arange(256)
+    assert (cv2.cvtColor(ramp.copy(), cv2.COLOR_BGR2GRAY) == mode_a.gray_from_rgb(ramp)).all()
+
+
+def test_rodrigues_roundtrip_against_cv2(golden):
+    cv2 = pytest.importorskip("cv2")
+    d = golden("dino12_scores")
+    for R in d["R"]:
+        want = cv2.Rodrigues(cv2.Rodrigues(R)[0])[0]
+        assert np.abs(rodrigues_roundtrip(R) - want).max() < 1e-13
+
+
+def test_known_answers():
+    # identical windows score n/(n-1) = 121/120 (MVS2.py:43 divides by n-1, np.std is the population std)
+    rng = np.random.default_rng(0)
+    a = rng.integers(0, 256, 121).astype(np.uint8)
+    assert abs(mode_a.ncc_literal(a, a) - 121 / 120) < 1e-12
+    assert abs(mode_a.ncc_literal(a, 255 - a) + 121 / 120) < 1e-12
+    assert np.isnan(mode_a.ncc_literal(a, np.full(121, 9, np.uint8)))      # zero variance -> NaN -> rejected
+    # bounds rule (HarrisFeatures.py:128): row 5 accepted, col 5 rejected, col 6 accepted
+    H, W = 40, 56
+    x = np.array([5.5, 6.5, 30.0, 30.0, W - 7 + 0.5, W - 6 + 0.5, 30.0, 30.0])
+    y = np.array([20.0, 20.0, 5.5, 4.5, 20.0, 20.0, H - 7 + 0.5, H - 6 + 0.5])
+    _, _, ok = mode_a.window_anchor(x, y, H, W, 5)
+    assert list(ok) == [False, True, True, False, True, False, True, False]
+    # truncation toward zero, non-finite rejected
+    r, c, ok = mode_a.window_anchor(np.array([-0.5, np.nan, np.inf]), np.array([-0.5, 1.0, 1.0]), H, W, 5)
+    assert r[0] == 0 and c[0] == 0 and not ok.any()
+
+
+def test_expansion_restatement_replays_reference_event_log(golden):
+    s, e = golden("dino12_scores"), golden("dino12_expansion")
+    gray = mode_a.gray_from_rgb(s["rgb"])
+    cams = _cams(s)
+    ns = int(e["n_seeds"])
+    seeds = [dict(c=e["c"][i], n=e["n"][i], vis=e["vis"][i], x=e["xy"][i, 0], y=e["xy"][i, 1]) for i in range(ns)]
+    table = e["table_before"].copy()
+    patches, events = expansion.expand_sequential(gray, cams, seeds, table, float(e["scale"]), int(e["bound"]),
+                                                  int(e["max_iter"]))
+    assert np.array_equal(np.array(events, dtype=np.int32), e["events"])     # same candidates, same accepts, same order
+    assert np.array_equal(table, e["table_after"])
+    got_c = np.array([p["c"] for p in patches[ns:]])
+    got_n = np.array([p["n"] for p in patches[ns:]])
+    assert np.abs(got_c - e["c"][ns:]).max() < 1e-14
+    assert np.abs(got_n - e["n"][ns:]).max() < 1e-14
+    assert np.array_equal(np.array([p["vis"] for p in patches[ns:]]), e["vis"][ns:])
+    assert np.abs(np.array([p["avg"] for p in patches[ns:]]) - e["avg"][ns:]).max() < 1e-12
+
+
+def test_round_expansion_is_deterministic_and_fills_cells(golden):
+    s, e = golden("dino12_scores"), golden("dino12_expansion")
+    gray = mode_a.gray_from_rgb(s["rgb"])
+    cams = _cams(s)
+    ns = int(e["n_seeds"])
+    fr = dict(c=e["c"][:ns], n=e["n"][:ns], vis=e["vis"][:ns], xy=e["xy"][:ns])
+    t1, t2 = e["table_before"].copy(), e["table_before"].copy()
+    c1, n1 = expansion.expand_round(gray, cams, fr, t1, float(e["scale"]), int(e["bound"]))
+    c2, n2 = expansion.expand_round(gray, cams, fr, t2, float(e["scale"]), int(e["bound"]))
+    assert np.array_equal(c1["accepted"], c2["accepted"]) and np.array_equal(t1, t2)
+    assert c1["accepted"].sum() > 0 and (~t1).sum() > (~e["table_before"]).sum()
+    assert len(np.unique(c1["slot"])) == len(c1["slot"]) and (np.diff(c1["slot"]) > 0).all()
+    # sibling rule: a dj=+1 slot is never accepted together with its dj=-1 sibling
+    acc = set(c1["slot"][c1["accepted"]].tolist())
+    assert not any((s_ & 1) and (s_ - 1) in acc for s_ in acc)
