@@ -106,6 +106,42 @@ int mvs_score_batch(mvs_ctx* ctx, int mode, int64_t N, const double* c, const do
                     double min_ncc, int wid, uint64_t* vis_mask, double* avg, int32_t* count, double* xy, float* ncc,
                     int on_device, void* stream);
 
+/*
+ * One accepted patch as exchanged between GPUs after a round: the fields of the
+ * reference's MyPatch (MVS2.py:45-60) that later rounds read.  A record is
+ * sizeof(mvs_patch_record) + 8*ceil(V/64) bytes: the struct followed by the visible
+ * set as a bit mask (patch.V; every entry shares xy, MVS2.py:74).
+ */
+typedef struct mvs_patch_record {
+    double c[3];   /* patch.c */
+    double n[3];   /* patch.n */
+    double xy[2];  /* x, y stored in every patch.V entry */
+    double avg;    /* patch.avg_ncc_score */
+    int32_t ref;   /* patch.R */
+    int32_t count; /* patch.visible_ct() */
+    int64_t index; /* global candidate index (deterministic order across GPUs) */
+} mvs_patch_record;
+
+/* Bytes per record for this context: sizeof(mvs_patch_record) + 8*ceil(V/64). */
+int mvs_record_bytes(const mvs_ctx* ctx);
+
+/*
+ * Keep the hypotheses that pass the caller-side accept test and pack them, in input
+ * order, into patch records.
+ * Replaces: the accept branch of patch_expansion (MVS2.py:369: visible_ct >= bound and
+ *           neighbour / distance tests; MVS2.py:401-403: enqueue) and of the seed loop
+ *           (MVS2.py:256-257), for a batch.
+ *   gate [N] uint8 or NULL: extra per-hypothesis condition computed by the caller side
+ *   keeps hypothesis i  <=>  count[i] >= bound && (gate == NULL || gate[i])
+ *   records   capacity * mvs_record_bytes() bytes; n_out receives the number kept
+ *             (records beyond capacity are counted but not written)
+ * All pointers are DEVICE pointers (n_out included); work is enqueued on `stream`.
+ */
+int mvs_compact_accepted(mvs_ctx* ctx, int64_t N, int64_t index_base, const double* c, const double* nrm,
+                         const int32_t* ref, const uint64_t* vis_mask, const double* avg, const int32_t* count,
+                         const double* xy, const uint8_t* gate, int bound, void* records, int64_t capacity,
+                         int64_t* n_out, void* stream);
+
 /* Number of kernels this library has launched on ctx since creation (for bench.py's
  * gpu_launches claim). */
 int64_t mvs_launch_count(const mvs_ctx* ctx);

@@ -20,6 +20,9 @@ SYMBOLS = {
     "mvs_score_batch": (C.c_int, [_P, C.c_int, C.c_int64, _P, _P, _P, C.c_double, C.c_int, _P, _P, _P, _P, _P,
                                   C.c_int, _P]),
     "mvs_launch_count": (C.c_int64, [_P]),
+    "mvs_record_bytes": (C.c_int, [_P]),
+    "mvs_compact_accepted": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, _P, C.c_int64,
+                                       _P, _P]),
 }
 
 _lib = None

@@ -1,0 +1,145 @@
+// K4a accept_compact: order-preserving stream compaction of accepted hypotheses into
+// fixed-size patch records (the payload of the per-round all-gather).
+//
+// Replaces the accept branch of the reference's expansion loop (MVS2.py:369,401-403:
+// "if visible_ct >= bound and ...: fill cells, enqueue") for a whole batch: a
+// hypothesis is kept iff count >= bound and its optional caller-side gate byte is
+// set.  Output order = input order (ascending global index), so the result does not
+// depend on how the batch was sharded across GPUs.
+//
+// Three small launches: per-tile counts, one-block exclusive scan, scatter.
+// HBM-bound; algorithmic bytes = 4 B/hypothesis read + record_bytes per accepted.
+#include "mvs_common.cuh"
+
+#define TILE 1024          // hypotheses per CTA (256 threads x 4)
+#define FULL 0xffffffffu
+
+__device__ __forceinline__ bool keep_flag(const int32_t* count, const uint8_t* gate, int bound, int64_t i, int64_t N) {
+    return i < N && count[i] >= bound && (gate == nullptr || gate[i] != 0);
+}
+
+__global__ void __launch_bounds__(256) compact_count(const int32_t* __restrict__ count, const uint8_t* __restrict__ gate,
+                                                     int bound, int64_t N, int32_t* __restrict__ tile_counts) {
+    __shared__ int warp_sum[8];
+    const int64_t base = (int64_t)blockIdx.x * TILE;
+    int k = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) k += keep_flag(count, gate, bound, base + j * 256 + threadIdx.x, N) ? 1 : 0;
+    k = __reduce_add_sync(FULL, k);
+    if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = k;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int s = 0;
+        for (int w = 0; w < 8; ++w) s += warp_sum[w];
+        tile_counts[blockIdx.x] = s;
+    }
+}
+
+// single CTA: exclusive scan of tile_counts[0..T) in place; total -> *n_out
+__global__ void __launch_bounds__(1024) compact_scan(int32_t* __restrict__ tile_counts, int T, int64_t* __restrict__ n_out) {
+    __shared__ int64_t carry;
+    __shared__ int wsum[32];
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int base = 0; base < T; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = (i < T) ? tile_counts[i] : 0;
+        int x = v;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            const int y = __shfl_up_sync(FULL, x, s);
+            if (lane >= s) x += y;
+        }
+        if (lane == 31) wsum[w] = x;
+        __syncthreads();
+        if (w == 0) {
+            int ws = wsum[lane];
+#pragma unroll
+            for (int s = 1; s < 32; s <<= 1) {
+                const int y = __shfl_up_sync(FULL, ws, s);
+                if (lane >= s) ws += y;
+            }
+            wsum[lane] = ws;
+        }
+        __syncthreads();
+        const int64_t excl = carry + (w > 0 ? wsum[w - 1] : 0) + (x - v);
+        if (i < T) tile_counts[i] = (int32_t)excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *n_out = carry;
+}
+
+__global__ void __launch_bounds__(256)
+    compact_scatter(const int32_t* __restrict__ count, const uint8_t* __restrict__ gate, int bound, int64_t N,
+                    const int32_t* __restrict__ tile_offsets, int64_t index_base, const double* __restrict__ c,
+                    const double* __restrict__ nrm, const int32_t* __restrict__ ref, const uint64_t* __restrict__ vis,
+                    const double* __restrict__ avg, const double* __restrict__ xy, int mw, uint8_t* __restrict__ records,
+                    int rec_bytes, int64_t capacity) {
+    __shared__ int warp_base[8];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t base = (int64_t)blockIdx.x * TILE;
+    int64_t out = tile_offsets[blockIdx.x];
+    for (int j = 0; j < 4; ++j) {
+        const int64_t i = base + j * 256 + threadIdx.x;
+        const bool k = keep_flag(count, gate, bound, i, N);
+        const unsigned b = __ballot_sync(FULL, k);
+        if (lane == 0) warp_base[w] = __popc(b);
+        __syncthreads();
+        int before = 0, total = 0;
+        for (int q = 0; q < 8; ++q) {
+            if (q < w) before += warp_base[q];
+            total += warp_base[q];
+        }
+        if (k) {
+            const int64_t dst = out + before + __popc(b & ((1u << lane) - 1u));
+            if (dst < capacity) {
+                mvs_patch_record* r = reinterpret_cast<mvs_patch_record*>(records + dst * rec_bytes);
+                r->c[0] = c[3 * i]; r->c[1] = c[3 * i + 1]; r->c[2] = c[3 * i + 2];
+                if (nrm) { r->n[0] = nrm[3 * i]; r->n[1] = nrm[3 * i + 1]; r->n[2] = nrm[3 * i + 2]; }
+                else { r->n[0] = r->n[1] = r->n[2] = 0.0; }
+                r->xy[0] = xy[2 * i]; r->xy[1] = xy[2 * i + 1];
+                r->avg = avg[i];
+                r->ref = ref[i];
+                r->count = count[i];
+                r->index = index_base + i;
+                uint64_t* rv = reinterpret_cast<uint64_t*>(r + 1);
+                for (int q = 0; q < mw; ++q) rv[q] = vis[i * mw + q];
+            }
+        }
+        out += total;
+        __syncthreads();
+    }
+}
+
+int mvs_launch_compact(mvs_ctx* ctx, int64_t N, int64_t index_base, const double* c, const double* nrm, const int32_t* ref,
+                       const uint64_t* vis, const double* avg, const int32_t* count, const double* xy, const uint8_t* gate,
+                       int bound, void* records, int64_t capacity, int64_t* d_n_out, cudaStream_t s) {
+    const int T = (int)((N + TILE - 1) / TILE);
+    if ((size_t)T * sizeof(int32_t) > ctx->tile_bytes) {
+        if (ctx->d_tiles) cudaFree(ctx->d_tiles);
+        ctx->d_tiles = nullptr;
+        ctx->tile_bytes = 0;
+        const size_t want = (size_t)T * sizeof(int32_t) * 2 + 4096;
+        if (cudaMalloc(&ctx->d_tiles, want) != cudaSuccess) {
+            cudaGetLastError();
+            mvs_set_error("compaction scratch allocation of %zu bytes failed", want);
+            return MVS_ERR_NOMEM;
+        }
+        ctx->tile_bytes = want;
+    }
+    const int mw = (ctx->V + 63) / 64;
+    if (T == 0) {
+        MVS_CUDA_CHECK(cudaMemsetAsync(d_n_out, 0, sizeof(int64_t), s));
+        return MVS_OK;
+    }
+    compact_count<<<T, 256, 0, s>>>(count, gate, bound, N, ctx->d_tiles);
+    compact_scan<<<1, 1024, 0, s>>>(ctx->d_tiles, T, d_n_out);
+    compact_scatter<<<T, 256, 0, s>>>(count, gate, bound, N, ctx->d_tiles, index_base, c, nrm, ref, vis, avg, xy, mw,
+                                      (uint8_t*)records, (int)(sizeof(mvs_patch_record) + 8 * mw), capacity);
+    ctx->launches += 3;
+    MVS_CUDA_CHECK(cudaGetLastError());
+    return MVS_OK;
+}

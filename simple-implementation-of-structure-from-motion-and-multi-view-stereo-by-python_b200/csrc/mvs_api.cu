@@ -222,6 +222,7 @@ extern "C" int mvs_destroy(mvs_ctx* ctx) {
     if (ctx->d_cam) cudaFree(ctx->d_cam);
     if (ctx->d_geom) cudaFree(ctx->d_geom);
     if (ctx->d_stage) cudaFree(ctx->d_stage);
+    if (ctx->d_tiles) cudaFree(ctx->d_tiles);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     free(ctx->h_rrt);
     free(ctx->h_centres);
@@ -305,4 +306,22 @@ extern "C" int mvs_score_batch(mvs_ctx* ctx, int mode, int64_t N, const double* 
     if (ncc) MVS_CUDA_CHECK(cudaMemcpyAsync(ncc, d_ncc, sizeof(float) * (size_t)V * N, cudaMemcpyDeviceToHost, s));
     MVS_CUDA_CHECK(cudaStreamSynchronize(s));
     return MVS_OK;
+}
+
+extern "C" int mvs_record_bytes(const mvs_ctx* ctx) {
+    return ctx ? (int)(sizeof(mvs_patch_record) + 8 * ((ctx->V + 63) / 64)) : 0;
+}
+
+extern "C" int mvs_compact_accepted(mvs_ctx* ctx, int64_t N, int64_t index_base, const double* c, const double* nrm,
+                                    const int32_t* ref, const uint64_t* vis_mask, const double* avg, const int32_t* count,
+                                    const double* xy, const uint8_t* gate, int bound, void* records, int64_t capacity,
+                                    int64_t* n_out, void* stream) {
+    if (!ctx) { mvs_set_error("mvs_compact_accepted: null context"); return MVS_ERR_ARG; }
+    if (N < 0 || capacity < 0 || !n_out || (N > 0 && (!c || !ref || !vis_mask || !avg || !count || !xy || !records))) {
+        mvs_set_error("mvs_compact_accepted: c, ref, vis_mask, avg, count, xy, records and n_out are required");
+        return MVS_ERR_ARG;
+    }
+    MVS_CUDA_CHECK(cudaSetDevice(ctx->device));
+    return mvs_launch_compact(ctx, N, index_base, c, nrm, ref, vis_mask, avg, count, xy, gate, bound, records, capacity,
+                              n_out, (cudaStream_t)stream);
 }

@@ -41,6 +41,9 @@ struct mvs_ctx {
     void* d_stage;
     size_t stage_bytes;
     cudaStream_t own_stream;
+    // compaction scratch
+    int32_t* d_tiles;
+    size_t tile_bytes;
 };
 
 void mvs_set_error(const char* fmt, ...);
@@ -59,3 +62,6 @@ void mvs_set_error(const char* fmt, ...);
 int mvs_launch_gray(mvs_ctx* ctx, const uint8_t* d_rgb, cudaStream_t s);
 int mvs_launch_score_refexact(mvs_ctx* ctx, int64_t N, const double* c, const int32_t* ref, double thr, int wid,
                               uint64_t* vis, double* avg, int32_t* count, double* xy, float* ncc, cudaStream_t s);
+int mvs_launch_compact(mvs_ctx* ctx, int64_t N, int64_t index_base, const double* c, const double* nrm, const int32_t* ref,
+                       const uint64_t* vis, const double* avg, const int32_t* count, const double* xy, const uint8_t* gate,
+                       int bound, void* records, int64_t capacity, int64_t* d_n_out, cudaStream_t s);
