@@ -228,7 +228,7 @@ def run_b200(args):
         if world > 1:
             dist.all_gather_into_tensor(counts, n_acc)
             mx = max(int(counts.max().item()), 1)                # host sync: payload size of this round
-            gathered = gbuf[: world * mx * rec_bytes].view(world, mx, rec_bytes)
+            gathered = gbuf[: world * mx * rec_bytes].view(world * mx, rec_bytes)
             dist.all_gather_into_tensor(gathered, records[:mx])
 
     def barrier():

@@ -119,7 +119,9 @@ typedef struct mvs_patch_record {
     double avg;    /* patch.avg_ncc_score */
     int32_t ref;   /* patch.R */
     int32_t count; /* patch.visible_ct() */
-    int64_t index; /* global candidate index (deterministic order across GPUs) */
+    int64_t index; /* global candidate index / expansion slot id (deterministic order across GPUs) */
+    int32_t px[2]; /* int(u), int(v) of the cell centre the patch was cast through: the pixel
+                      CellTable.get_color reads (MVS2.py:116-117,357); -1 when not applicable */
 } mvs_patch_record;
 
 /* Bytes per record for this context: sizeof(mvs_patch_record) + 8*ceil(V/64). */
@@ -141,6 +143,58 @@ int mvs_compact_accepted(mvs_ctx* ctx, int64_t N, int64_t index_base, const doub
                          const int32_t* ref, const uint64_t* vis_mask, const double* avg, const int32_t* count,
                          const double* xy, const uint8_t* gate, int bound, void* records, int64_t capacity,
                          int64_t* n_out, void* stream);
+
+/*
+ * Cell table (CellTable, MVS2.py:80-120): one vacancy byte per (view, x-cell, y-cell),
+ * shape [V, ceil((W-1)/cs), ceil((H-1)/cs)] exactly as the reference's list of bool
+ * arrays (MVS2.py:88), 1 = vacant.  table_host NULL = all vacant.
+ */
+int mvs_cells_init(mvs_ctx* ctx, int cell_size, const uint8_t* table_host);
+int mvs_cells_shape(const mvs_ctx* ctx, int* cell_size, int* wc, int* hc);
+int mvs_cells_download(mvs_ctx* ctx, uint8_t* table_host);
+
+/*
+ * CellTable.fill_with_point (MVS2.py:98-107) for a batch of patch records: clears cell
+ * (v, floor(x/cs), floor(y/cs)) for every view v in the record's visible set.
+ * records: DEVICE pointer to n records.
+ */
+int mvs_cells_fill(mvs_ctx* ctx, const void* records, int64_t n, void* stream);
+
+/*
+ * One synchronous expansion round, phase 1: candidate generation.
+ * Replaces: patch_expansion's candidate loop (MVS2.py:328-361) for a whole frontier.
+ * For every frontier patch f, every view v in its visible set and every diagonal
+ * k = (di,dj) in ((-1,-1),(-1,1),(1,-1),(1,1)): slot s = (f*V + v)*4 + k is live when
+ * cell (v, ci+di, cj+dj) is vacant in the round-start table (MVS2.py:333); among live
+ * slots testing the same cell only the lowest s survives.  Survivors become candidates
+ * in ascending slot order with c = ray/plane hit (MVS2.py:334-356, including the
+ * reference's (ci+di, cj+di) pixel and "+C" ray quirks), n = (O-c)/|O-c|, ref = v.
+ *   frontier  DEVICE pointer to F patch records
+ *   n_candidates  HOST pointer; the call synchronises `stream` to produce it
+ * The candidate arrays stay inside the context until the next generate call.
+ */
+int mvs_round_generate(mvs_ctx* ctx, const void* frontier, int64_t F, int64_t* n_candidates, void* stream);
+
+/*
+ * Phase 2: score candidates [begin, end) (this GPU's shard) with Mode A, apply the
+ * accept test of MVS2.py:369 (visible_ct >= bound, is_patch_neighbor(thr 0.1),
+ * distance(parent.c, c) < 0.05/scale) and pack the passing ones, in slot order, into
+ * records (index = slot id).  records/n_out: DEVICE pointers.
+ */
+int mvs_round_score(mvs_ctx* ctx, const void* frontier, int64_t begin, int64_t end, double min_ncc, int wid, int bound,
+                    double scale, void* records, int64_t capacity, int64_t* n_out, void* stream);
+
+/*
+ * Phase 3 (identical on every GPU, on the gathered records of ALL shards in ascending
+ * slot order): drop a dj=+1 record whose dj=-1 sibling (slot-1) also passed -- the
+ * `break` of MVS2.py:404 --, fill the cells of the kept ones (MVS2.py:401-402) and
+ * write them as the next frontier.  All pointers DEVICE pointers.
+ */
+int mvs_round_commit(mvs_ctx* ctx, const void* records, int64_t n, void* next_frontier, int64_t* n_next, void* stream);
+
+/* Debug/parity access to the candidates of the last mvs_round_generate: any pointer may be
+ * NULL; HOST pointers.  slot [M] int64, parent [M] int64, c [M,3], nrm [M,3], ref [M] int32. */
+int mvs_round_candidates(mvs_ctx* ctx, int64_t* slot, int64_t* parent, double* c, double* nrm, int32_t* ref);
 
 /* Number of kernels this library has launched on ctx since creation (for bench.py's
  * gpu_launches claim). */

@@ -159,40 +159,63 @@ def round_slots(frontier_vis, frontier_xy, table, cs):
     return out
 
 
+def round_generate(cams, frontier, table, cs=2):
+    """Phase 1 of a round: live, de-duplicated slots -> candidate geometry (slot order)."""
+    centres = cams.centres()
+    slots = round_slots(frontier["vis"], frontier["xy"], table, cs)
+    M = len(slots)
+    cand = dict(slot=np.zeros(M, np.int64), parent=np.zeros(M, np.int64), c=np.zeros((M, 3)), n=np.zeros((M, 3)),
+                ref=np.zeros(M, np.int32), uv=np.zeros((M, 2)))
+    for m, (s, f, view, k, ci, cj) in enumerate(slots):
+        X, n, u, v = candidate(cams, centres, frontier["c"][f], frontier["n"][f], view, ci, cj, DIAG[k][0], cs)
+        cand["slot"][m], cand["parent"][m], cand["c"][m], cand["n"][m], cand["ref"][m] = s, f, X, n, view
+        cand["uv"][m] = (u, v)
+    return cand
+
+
+def round_score(gray, cams, frontier, cand, begin, end, scale, bound, thr=0.7, wid=5):
+    """Phase 2 for candidates [begin, end): Mode A score + the accept test of MVS2.py:369."""
+    V = gray.shape[0]
+    n = end - begin
+    out = dict(vis=np.zeros((n, V), bool), count=np.zeros(n, np.int32), avg=np.zeros(n), xy=np.full((n, 2), np.nan),
+               passed=np.zeros(n, bool))
+    X = cand["c"][begin:end]
+    fin = np.isfinite(X).all(1)                  # non-finite centres are rejected (declared divergence)
+    if fin.any():
+        o = mode_a.score(gray, cams, X[fin], cand["ref"][begin:end][fin], thr, wid)
+        out["vis"][fin], out["count"][fin], out["avg"][fin] = o["vis"], o["count"], o["avg"]
+        out["xy"][fin] = np.stack([o["x"], o["y"]], 1)
+    for i, m in enumerate(range(begin, end)):
+        f = cand["parent"][m]
+        out["passed"][i] = accept(frontier["c"][f], frontier["n"][f], cand["c"][m], cand["n"][m], out["count"][i], bound, scale)
+    return out
+
+
+def round_commit(slots, xy, vis, table, cs=2):
+    """Phase 3 on the passed records of ALL shards (ascending slot): sibling rule
+    (the ``break`` of MVS2.py:404), then cell fills (MVS2.py:401-402).  Returns keep flags."""
+    slots = np.asarray(slots)
+    present = set(slots.tolist())
+    keep = np.array([not ((s & 1) and (s - 1) in present) for s in slots.tolist()], dtype=bool)
+    for i in np.nonzero(keep)[0]:
+        fx, fy = which_cell(xy[i, 0], xy[i, 1], cs)
+        for hv in np.nonzero(vis[i])[0]:
+            table[hv, fx, fy] = False
+    return keep
+
+
 def expand_round(gray, cams, frontier, table, scale, bound, cs=2, thr=0.7, wid=5):
     """One synchronous round.  frontier: dict of arrays c [F,3], n [F,3], vis [F,V],
     xy [F,2].  ``table`` is mutated by the commit.  Returns dict with the candidate
     list (slot order), per-candidate scores, the accept flags and the next frontier."""
-    centres = cams.centres()
-    V = gray.shape[0]
-    slots = round_slots(frontier["vis"], frontier["xy"], table, cs)
-    M = len(slots)
-    cand = dict(slot=np.zeros(M, np.int64), c=np.zeros((M, 3)), n=np.zeros((M, 3)), ref=np.zeros(M, np.int32),
-                uv=np.zeros((M, 2)), vis=np.zeros((M, V), bool), count=np.zeros(M, np.int32), avg=np.zeros(M),
-                xy=np.zeros((M, 2)), passed=np.zeros(M, bool), accepted=np.zeros(M, bool))
-    by_slot = {}
-    for m, (s, f, view, k, ci, cj) in enumerate(slots):
-        di, dj = DIAG[k]
-        X, n, u, v = candidate(cams, centres, frontier["c"][f], frontier["n"][f], view, ci, cj, di, cs)
-        sc = _score_one(gray, cams, X, view, thr, wid)
-        cand["slot"][m], cand["c"][m], cand["n"][m], cand["ref"][m] = s, X, n, view
-        cand["uv"][m] = (u, v)
-        cand["vis"][m], cand["count"][m], cand["avg"][m] = sc["vis"], sc["count"], sc["avg"]
-        cand["xy"][m] = (sc["x"], sc["y"])
-        cand["passed"][m] = accept(frontier["c"][f], frontier["n"][f], X, n, sc["count"], bound, scale)
-        by_slot[s] = m
-    for m, (s, f, view, k, ci, cj) in enumerate(slots):
-        ok = cand["passed"][m]
-        if ok and (k & 1):                      # dj = +1: dropped when the dj = -1 sibling passed (the ``break``)
-            sib = by_slot.get(s - 1)
-            if sib is not None and cand["passed"][sib]:
-                ok = False
-        cand["accepted"][m] = ok
+    cand = round_generate(cams, frontier, table, cs)
+    M = len(cand["slot"])
+    cand.update(round_score(gray, cams, frontier, cand, 0, M, scale, bound, thr, wid))
+    p = np.nonzero(cand["passed"])[0]
+    keep = round_commit(cand["slot"][p], cand["xy"][p], cand["vis"][p], table, cs)
+    cand["accepted"] = np.zeros(M, bool)
+    cand["accepted"][p[keep]] = True
     acc = np.nonzero(cand["accepted"])[0]
-    for m in acc:                               # commit in slot order
-        fx, fy = which_cell(cand["xy"][m, 0], cand["xy"][m, 1], cs)
-        for hv in np.nonzero(cand["vis"][m])[0]:
-            table[hv, fx, fy] = False
     nxt = dict(c=cand["c"][acc], n=cand["n"][acc], vis=cand["vis"][acc], xy=cand["xy"][acc],
                ref=cand["ref"][acc], avg=cand["avg"][acc])
     return cand, nxt

@@ -21,6 +21,15 @@ SYMBOLS = {
                                   C.c_int, _P]),
     "mvs_launch_count": (C.c_int64, [_P]),
     "mvs_record_bytes": (C.c_int, [_P]),
+    "mvs_cells_init": (C.c_int, [_P, C.c_int, _P]),
+    "mvs_cells_shape": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "mvs_cells_download": (C.c_int, [_P, _P]),
+    "mvs_cells_fill": (C.c_int, [_P, _P, C.c_int64, _P]),
+    "mvs_round_generate": (C.c_int, [_P, _P, C.c_int64, C.POINTER(C.c_int64), _P]),
+    "mvs_round_score": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_double, C.c_int, C.c_int, C.c_double, _P, C.c_int64,
+                                  _P, _P]),
+    "mvs_round_commit": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P]),
+    "mvs_round_candidates": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "mvs_compact_accepted": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, _P, C.c_int64,
                                        _P, _P]),
 }

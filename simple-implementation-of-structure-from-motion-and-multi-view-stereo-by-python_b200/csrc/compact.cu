@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(256)
                     const int32_t* __restrict__ tile_offsets, int64_t index_base, const double* __restrict__ c,
                     const double* __restrict__ nrm, const int32_t* __restrict__ ref, const uint64_t* __restrict__ vis,
                     const double* __restrict__ avg, const double* __restrict__ xy, int mw, uint8_t* __restrict__ records,
-                    int rec_bytes, int64_t capacity) {
+                    int rec_bytes, int64_t capacity, const int64_t* __restrict__ index_arr, const int32_t* __restrict__ px) {
     __shared__ int warp_base[8];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t base = (int64_t)blockIdx.x * TILE;
@@ -104,7 +104,9 @@ __global__ void __launch_bounds__(256)
                 r->avg = avg[i];
                 r->ref = ref[i];
                 r->count = count[i];
-                r->index = index_base + i;
+                r->index = index_arr ? index_arr[i] : index_base + i;
+                r->px[0] = px ? px[2 * i] : -1;
+                r->px[1] = px ? px[2 * i + 1] : -1;
                 uint64_t* rv = reinterpret_cast<uint64_t*>(r + 1);
                 for (int q = 0; q < mw; ++q) rv[q] = vis[i * mw + q];
             }
@@ -116,7 +118,8 @@ __global__ void __launch_bounds__(256)
 
 int mvs_launch_compact(mvs_ctx* ctx, int64_t N, int64_t index_base, const double* c, const double* nrm, const int32_t* ref,
                        const uint64_t* vis, const double* avg, const int32_t* count, const double* xy, const uint8_t* gate,
-                       int bound, void* records, int64_t capacity, int64_t* d_n_out, cudaStream_t s) {
+                       int bound, void* records, int64_t capacity, int64_t* d_n_out, const int64_t* index_arr,
+                       const int32_t* px, cudaStream_t s) {
     const int T = (int)((N + TILE - 1) / TILE);
     if ((size_t)T * sizeof(int32_t) > ctx->tile_bytes) {
         if (ctx->d_tiles) cudaFree(ctx->d_tiles);
@@ -138,7 +141,7 @@ int mvs_launch_compact(mvs_ctx* ctx, int64_t N, int64_t index_base, const double
     compact_count<<<T, 256, 0, s>>>(count, gate, bound, N, ctx->d_tiles);
     compact_scan<<<1, 1024, 0, s>>>(ctx->d_tiles, T, d_n_out);
     compact_scatter<<<T, 256, 0, s>>>(count, gate, bound, N, ctx->d_tiles, index_base, c, nrm, ref, vis, avg, xy, mw,
-                                      (uint8_t*)records, (int)(sizeof(mvs_patch_record) + 8 * mw), capacity);
+                                      (uint8_t*)records, (int)(sizeof(mvs_patch_record) + 8 * mw), capacity, index_arr, px);
     ctx->launches += 3;
     MVS_CUDA_CHECK(cudaGetLastError());
     return MVS_OK;

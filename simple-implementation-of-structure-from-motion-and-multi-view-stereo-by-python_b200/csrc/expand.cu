@@ -1,0 +1,382 @@
+// K3 expand_candidates + K4 accept/commit: the reference's patch_expansion
+// (MVS2.py:308-404) restructured into synchronous rounds, and its CellTable
+// (MVS2.py:80-120) as a byte grid in HBM.
+//
+// Round semantics (DESIGN.md "Rounds"; oracle/expansion.py::expand_round is the CPU
+// restatement): every frontier patch is expanded against the ROUND-START table; slots
+// s = (f*V + v)*4 + k are de-duplicated per tested cell (lowest s wins, by an epoch-
+// tagged atomicMax so the claim grid never needs clearing); survivors are scored and
+// gated; accepted records are committed in slot order.  All fp64 geometry uses
+// explicit round-to-nearest intrinsics (no FMA contraction) so that candidates are
+// bit-identical to the NumPy oracle and hence truncate to the same pixels.
+#include "scan.cuh"
+
+#define FULL 0xffffffffu
+
+__device__ __forceinline__ double xmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double xadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double xsub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double xdiv(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ double dot3(double a0, double a1, double a2, double b0, double b1, double b2) {
+    return xadd(xadd(xmul(a0, b0), xmul(a1, b1)), xmul(a2, b2));
+}
+
+__device__ __forceinline__ const mvs_patch_record* rec_at(const uint8_t* base, int64_t i, int rec_bytes) {
+    return reinterpret_cast<const mvs_patch_record*>(base + i * rec_bytes);
+}
+__device__ __forceinline__ const uint64_t* rec_vis(const mvs_patch_record* r) {
+    return reinterpret_cast<const uint64_t*>(r + 1);
+}
+
+// CellTable.which_cell (MVS2.py:113-114): floor(x / cell_size) in fp64
+__device__ __forceinline__ bool which_cell(double x, double y, int cs, int& ci, int& cj) {
+    if (!(isfinite(x) && isfinite(y))) return false;
+    const double fi = floor(xdiv(x, (double)cs)), fj = floor(xdiv(y, (double)cs));
+    if (fabs(fi) > 1e9 || fabs(fj) > 1e9) return false;
+    ci = (int)fi;
+    cj = (int)fj;
+    return true;
+}
+
+__constant__ int c_di[4] = {-1, -1, 1, 1};      // loop order of MVS2.py:331-332
+__constant__ int c_dj[4] = {-1, 1, -1, 1};
+
+// claim value: newer epochs always win over stale ones; inside an epoch the LOWEST slot wins
+__device__ __forceinline__ unsigned long long claim_value(unsigned epoch, long long slot) {
+    return ((unsigned long long)epoch << 40) | (unsigned long long)((1ll << 40) - 1 - slot);
+}
+
+// pass 0: claim cells; pass 1: count surviving slots; pass 2: emit candidates
+template <int PASS>
+__global__ void __launch_bounds__(128)
+    expand_slots(const uint8_t* __restrict__ frontier, int64_t F, int rec_bytes, int V, int cs, int wc, int hc,
+                 const uint8_t* __restrict__ cells, unsigned long long* __restrict__ claim, unsigned epoch,
+                 int32_t* __restrict__ counts /*[F]*/, const CamGeom* __restrict__ geom, int64_t* __restrict__ cand_slot,
+                 int64_t* __restrict__ cand_parent, double* __restrict__ cand_c, double* __restrict__ cand_n,
+                 int32_t* __restrict__ cand_ref, int32_t* __restrict__ cand_px) {
+    const int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    const mvs_patch_record* p = rec_at(frontier, f, rec_bytes);
+    const uint64_t* vis = rec_vis(p);
+    int ci, cj;
+    int n_live = 0;
+    int64_t out = (PASS == 2) ? (int64_t)counts[f] : 0;
+    if (which_cell(p->xy[0], p->xy[1], cs, ci, cj)) {
+        const int mw = (V + 63) >> 6;
+        for (int w = 0; w < mw; ++w) {
+            uint64_t bits = vis[w];
+            while (bits) {
+                const int v = w * 64 + __ffsll((long long)bits) - 1;
+                bits &= bits - 1;
+                if (v >= V) break;
+                for (int k = 0; k < 4; ++k) {
+                    const int ti = ci + c_di[k], tj = cj + c_dj[k];
+                    if (ti < 0 || ti >= wc || tj < 0 || tj >= hc) continue;              // is_vacant: out of range
+                    const int64_t cell = ((int64_t)v * wc + ti) * hc + tj;
+                    if (!cells[cell]) continue;                                          // MVS2.py:333
+                    const long long slot = ((long long)f * V + v) * 4 + k;
+                    const unsigned long long mine = claim_value(epoch, slot);
+                    if (PASS == 0) {
+                        atomicMax(claim + cell, mine);
+                        continue;
+                    }
+                    if (claim[cell] != mine) continue;                                   // a lower slot tests this cell
+                    if (PASS == 1) {
+                        ++n_live;
+                        continue;
+                    }
+                    // ---- PASS 2: candidate geometry, MVS2.py:334-358 -----------------------------
+                    const CamGeom& g = geom[v];
+                    const int di = c_di[k];
+                    const double u = xmul((double)cs, xadd((double)(ci + di), 0.5));
+                    const double vv = xmul((double)cs, xadd((double)(cj + di), 0.5));      // sic: di on both axes
+                    const double a0 = xsub(u, g.cx), a1 = xsub(vv, g.cy), a2 = xdiv(xadd(g.fx, g.fy), 2.0);
+                    // R^T a + C  (sic: "+ C", MVS2.py:353)
+                    const double P0 = xadd(dot3(g.rf[0], g.rf[3], g.rf[6], a0, a1, a2), g.C[0]);
+                    const double P1 = xadd(dot3(g.rf[1], g.rf[4], g.rf[7], a0, a1, a2), g.C[1]);
+                    const double P2 = xadd(dot3(g.rf[2], g.rf[5], g.rf[8], a0, a1, a2), g.C[2]);
+                    const double nrm = sqrt(dot3(P0, P1, P2, P0, P1, P2));
+                    const double d0 = xdiv(P0, nrm), d1 = xdiv(P1, nrm), d2 = xdiv(P2, nrm);
+                    // ray_plane_intersection (MVS2.py:302-306) with origin O = C
+                    const double dot_out = dot3(d0, d1, d2, p->n[0], p->n[1], p->n[2]);
+                    const double w0 = xsub(p->c[0], g.C[0]), w1 = xsub(p->c[1], g.C[1]), w2 = xsub(p->c[2], g.C[2]);
+                    const double tpar = xdiv(dot3(w0, w1, w2, p->n[0], p->n[1], p->n[2]), dot_out);
+                    const double X0 = xadd(g.C[0], xmul(tpar, d0)), X1 = xadd(g.C[1], xmul(tpar, d1)),
+                                 X2 = xadd(g.C[2], xmul(tpar, d2));
+                    const double q0 = xsub(g.C[0], X0), q1 = xsub(g.C[1], X1), q2 = xsub(g.C[2], X2);
+                    const double dist = sqrt(dot3(q0, q1, q2, q0, q1, q2));
+                    cand_slot[out] = slot;
+                    cand_parent[out] = f;
+                    cand_c[3 * out] = X0; cand_c[3 * out + 1] = X1; cand_c[3 * out + 2] = X2;
+                    cand_n[3 * out] = xdiv(q0, dist); cand_n[3 * out + 1] = xdiv(q1, dist); cand_n[3 * out + 2] = xdiv(q2, dist);
+                    cand_ref[out] = v;
+                    cand_px[2 * out] = (int)u;
+                    cand_px[2 * out + 1] = (int)vv;
+                    ++out;
+                }
+            }
+        }
+    }
+    if (PASS == 1) counts[f] = n_live;
+}
+
+// accept gate of MVS2.py:369 without the visible_ct clause (applied by the compaction):
+// is_patch_neighbor(parent, cand, 0.1) and distance(parent.c, cand.c) < 0.05/scale
+__global__ void __launch_bounds__(256)
+    expand_gate(const uint8_t* __restrict__ frontier, int rec_bytes, int64_t begin, int64_t end,
+                const int64_t* __restrict__ cand_parent, const double* __restrict__ cand_c,
+                const double* __restrict__ cand_n, double dist_limit, uint8_t* __restrict__ gate) {
+    const int64_t m = begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (m >= end) return;
+    const mvs_patch_record* p = rec_at(frontier, cand_parent[m], rec_bytes);
+    const double w0 = xsub(p->c[0], cand_c[3 * m]), w1 = xsub(p->c[1], cand_c[3 * m + 1]), w2 = xsub(p->c[2], cand_c[3 * m + 2]);
+    const double a = dot3(w0, w1, w2, p->n[0], p->n[1], p->n[2]);
+    const double b = dot3(w0, w1, w2, cand_n[3 * m], cand_n[3 * m + 1], cand_n[3 * m + 2]);
+    const bool neigh = fabs(xadd(a, b)) < 0.1;
+    const double dist = sqrt(dot3(w0, w1, w2, w0, w1, w2));
+    gate[m] = (neigh && dist < dist_limit) ? 1 : 0;          // NaN compares false, as in Python
+}
+
+// commit, step 1: keep[i] = 0 for a dj=+1 record whose dj=-1 sibling (slot-1) is the previous record
+__global__ void __launch_bounds__(256)
+    commit_flags(const uint8_t* __restrict__ recs, int64_t n, int rec_bytes, int32_t* __restrict__ keep) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long slot = rec_at(recs, i, rec_bytes)->index;
+    bool k = true;
+    if ((slot & 1) && i > 0 && rec_at(recs, i - 1, rec_bytes)->index == slot - 1) k = false;
+    keep[i] = k ? 1 : 0;
+}
+
+// commit, step 2: copy kept records to the next frontier (order preserved) and clear their cells
+__global__ void __launch_bounds__(256)
+    commit_apply(const uint8_t* __restrict__ recs, int64_t n, int rec_bytes, const int32_t* __restrict__ offsets,
+                 const int64_t* __restrict__ total, uint8_t* __restrict__ next, int V, int cs, int wc, int hc,
+                 uint8_t* __restrict__ cells) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t off = offsets[i];
+    const int64_t nxt = (i + 1 < n) ? (int64_t)offsets[i + 1] : *total;
+    if (nxt == off) return;                                   // dropped sibling
+    const mvs_patch_record* r = rec_at(recs, i, rec_bytes);
+    if (next) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(r);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(next + off * rec_bytes);
+        for (int q = 0; q < rec_bytes / 4; ++q) dst[q] = src[q];
+    }
+    int ci, cj;
+    if (!which_cell(r->xy[0], r->xy[1], cs, ci, cj)) return;
+    if (ci < 0 || ci >= wc || cj < 0 || cj >= hc) return;     // the reference would stop in pdb here
+    const uint64_t* vis = rec_vis(r);
+    for (int w = 0; w < (V + 63) / 64; ++w) {
+        uint64_t bits = vis[w];
+        while (bits) {
+            const int v = w * 64 + __ffsll((long long)bits) - 1;
+            bits &= bits - 1;
+            if (v < V) cells[((int64_t)v * wc + ci) * hc + cj] = 0;     // MVS2.py:105
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+    cells_fill_kernel(const uint8_t* __restrict__ recs, int64_t n, int rec_bytes, int V, int cs, int wc, int hc,
+                      uint8_t* __restrict__ cells) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const mvs_patch_record* r = rec_at(recs, i, rec_bytes);
+    int ci, cj;
+    if (!which_cell(r->xy[0], r->xy[1], cs, ci, cj)) return;
+    if (ci < 0 || ci >= wc || cj < 0 || cj >= hc) return;
+    const uint64_t* vis = rec_vis(r);
+    for (int w = 0; w < (V + 63) / 64; ++w) {
+        uint64_t bits = vis[w];
+        while (bits) {
+            const int v = w * 64 + __ffsll((long long)bits) - 1;
+            bits &= bits - 1;
+            if (v < V) cells[((int64_t)v * wc + ci) * hc + cj] = 0;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+static int rec_bytes_of(const mvs_ctx* ctx) { return (int)(sizeof(mvs_patch_record) + 8 * ((ctx->V + 63) / 64)); }
+
+extern "C" int mvs_cells_init(mvs_ctx* ctx, int cell_size, const uint8_t* table_host) {
+    if (!ctx || cell_size < 1) { mvs_set_error("mvs_cells_init: bad argument"); return MVS_ERR_ARG; }
+    MVS_CUDA_CHECK(cudaSetDevice(ctx->device));
+    ctx->cell_size = cell_size;
+    ctx->wc = (ctx->W - 1 + cell_size - 1) / cell_size;       // ceil((W-1)/cs), MVS2.py:88
+    ctx->hc = (ctx->H - 1 + cell_size - 1) / cell_size;
+    const size_t ncell = (size_t)ctx->V * ctx->wc * ctx->hc;
+    int rc = mvs_ensure((void**)&ctx->d_cells, &ctx->cells_bytes, ncell + 16, "cell table");
+    if (rc != MVS_OK) return rc;
+    rc = mvs_ensure((void**)&ctx->d_claim, &ctx->claim_bytes, ncell * sizeof(unsigned long long), "claim grid");
+    if (rc != MVS_OK) return rc;
+    if (table_host)
+        MVS_CUDA_CHECK(cudaMemcpy(ctx->d_cells, table_host, ncell, cudaMemcpyHostToDevice));
+    else
+        MVS_CUDA_CHECK(cudaMemset(ctx->d_cells, 1, ncell));
+    MVS_CUDA_CHECK(cudaMemset(ctx->d_claim, 0, ncell * sizeof(unsigned long long)));
+    ctx->epoch = 0;
+    ctx->n_cand = 0;
+    return MVS_OK;
+}
+
+extern "C" int mvs_cells_shape(const mvs_ctx* ctx, int* cell_size, int* wc, int* hc) {
+    if (!ctx || !ctx->d_cells) { mvs_set_error("cell table not initialised"); return MVS_ERR_STATE; }
+    if (cell_size) *cell_size = ctx->cell_size;
+    if (wc) *wc = ctx->wc;
+    if (hc) *hc = ctx->hc;
+    return MVS_OK;
+}
+
+extern "C" int mvs_cells_download(mvs_ctx* ctx, uint8_t* table_host) {
+    if (!ctx || !ctx->d_cells || !table_host) { mvs_set_error("cell table not initialised"); return MVS_ERR_STATE; }
+    MVS_CUDA_CHECK(cudaSetDevice(ctx->device));
+    MVS_CUDA_CHECK(cudaDeviceSynchronize());
+    MVS_CUDA_CHECK(cudaMemcpy(table_host, ctx->d_cells, (size_t)ctx->V * ctx->wc * ctx->hc, cudaMemcpyDeviceToHost));
+    return MVS_OK;
+}
+
+extern "C" int mvs_cells_fill(mvs_ctx* ctx, const void* records, int64_t n, void* stream) {
+    if (!ctx || !ctx->d_cells) { mvs_set_error("cell table not initialised"); return MVS_ERR_STATE; }
+    if (n < 0 || (n > 0 && !records)) { mvs_set_error("mvs_cells_fill: bad argument"); return MVS_ERR_ARG; }
+    if (n == 0) return MVS_OK;
+    MVS_CUDA_CHECK(cudaSetDevice(ctx->device));
+    cells_fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        (const uint8_t*)records, n, rec_bytes_of(ctx), ctx->V, ctx->cell_size, ctx->wc, ctx->hc, ctx->d_cells);
+    ctx->launches++;
+    MVS_CUDA_CHECK(cudaGetLastError());
+    return MVS_OK;
+}
+
+static int ensure_candidates(mvs_ctx* ctx, int64_t M) {
+    const size_t mw = (size_t)((ctx->V + 63) / 64);
+    int rc;
+    if ((rc = mvs_ensure((void**)&ctx->cand_slot, &ctx->cand_cap[0], sizeof(int64_t) * M, "candidates")) != MVS_OK) return rc;
+    if ((rc = mvs_ensure((void**)&ctx->cand_parent, &ctx->cand_cap[1], sizeof(int64_t) * M, "candidates")) != MVS_OK) return rc;
+    if ((rc = mvs_ensure((void**)&ctx->cand_c, &ctx->cand_cap[2], sizeof(double) * 3 * M, "candidates")) != MVS_OK) return rc;
+    if ((rc = mvs_ensure((void**)&ctx->cand_n, &ctx->cand_cap[3], sizeof(double) * 3 * M, "candidates")) != MVS_OK) return rc;
+    if ((rc = mvs_ensure((void**)&ctx->cand_ref, &ctx->cand_cap[4], sizeof(int32_t) * M, "candidates")) != MVS_OK) return rc;
+    if ((rc = mvs_ensure((void**)&ctx->cand_px, &ctx->cand_cap[5], sizeof(int32_t) * 2 * M, "candidates")) != MVS_OK) return rc;
+    if ((rc = mvs_ensure((void**)&ctx->cand_vis, &ctx->cand_cap[6], sizeof(uint64_t) * mw * M, "scores")) != MVS_OK) return rc;
+    if ((rc = mvs_ensure((void**)&ctx->cand_avg, &ctx->cand_cap[7], sizeof(double) * M, "scores")) != MVS_OK) return rc;
+    if ((rc = mvs_ensure((void**)&ctx->cand_count, &ctx->cand_cap[8], sizeof(int32_t) * M, "scores")) != MVS_OK) return rc;
+    if ((rc = mvs_ensure((void**)&ctx->cand_xy, &ctx->cand_cap[9], sizeof(double) * 2 * M, "scores")) != MVS_OK) return rc;
+    if ((rc = mvs_ensure((void**)&ctx->cand_gate, &ctx->cand_cap[10], M, "gate")) != MVS_OK) return rc;
+    return MVS_OK;
+}
+
+extern "C" int mvs_round_generate(mvs_ctx* ctx, const void* frontier, int64_t F, int64_t* n_candidates, void* stream) {
+    if (!ctx || !ctx->d_cells) { mvs_set_error("mvs_round_generate: cell table not initialised"); return MVS_ERR_STATE; }
+    if (F < 0 || !n_candidates || (F > 0 && !frontier)) { mvs_set_error("mvs_round_generate: bad argument"); return MVS_ERR_ARG; }
+    MVS_CUDA_CHECK(cudaSetDevice(ctx->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    ctx->n_cand = 0;
+    *n_candidates = 0;
+    if (F == 0) return MVS_OK;
+    if (F * (int64_t)ctx->V * 4 >= (1ll << 40)) { mvs_set_error("frontier too large for the slot encoding"); return MVS_ERR_ARG; }
+    int rc;
+    if ((rc = mvs_ensure((void**)&ctx->d_counts, &ctx->counts_bytes, sizeof(int32_t) * F, "slot counts")) != MVS_OK) return rc;
+    if ((rc = mvs_ensure((void**)&ctx->d_scan, &ctx->scan_bytes, sizeof(int64_t) * ((F + 1023) / 1024 + 2), "scan")) != MVS_OK) return rc;
+    ctx->epoch++;
+    const int rb = rec_bytes_of(ctx);
+    const unsigned blocks = (unsigned)((F + 127) / 128);
+    int64_t* d_total = ctx->d_scan + (F + 1023) / 1024;
+    expand_slots<0><<<blocks, 128, 0, s>>>((const uint8_t*)frontier, F, rb, ctx->V, ctx->cell_size, ctx->wc, ctx->hc, ctx->d_cells,
+                                          ctx->d_claim, ctx->epoch, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                          nullptr, nullptr);
+    expand_slots<1><<<blocks, 128, 0, s>>>((const uint8_t*)frontier, F, rb, ctx->V, ctx->cell_size, ctx->wc, ctx->hc, ctx->d_cells,
+                                          ctx->d_claim, ctx->epoch, ctx->d_counts, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                          nullptr, nullptr);
+    ctx->launches += 2;
+    MVS_CUDA_CHECK(cudaGetLastError());
+    if ((rc = mvs_exclusive_scan_i32(ctx->d_counts, F, ctx->d_scan, d_total, s)) != MVS_OK) return rc;
+    ctx->launches += 3;
+    int64_t M = 0;
+    MVS_CUDA_CHECK(cudaMemcpyAsync(&M, d_total, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    MVS_CUDA_CHECK(cudaStreamSynchronize(s));
+    if (M >= (1ll << 31)) { mvs_set_error("more than 2^31 candidates in one round"); return MVS_ERR_ARG; }
+    if (M > 0) {
+        if ((rc = ensure_candidates(ctx, M)) != MVS_OK) return rc;
+        expand_slots<2><<<blocks, 128, 0, s>>>((const uint8_t*)frontier, F, rb, ctx->V, ctx->cell_size, ctx->wc, ctx->hc,
+                                              ctx->d_cells, ctx->d_claim, ctx->epoch, ctx->d_counts, ctx->d_geom, ctx->cand_slot,
+                                              ctx->cand_parent, ctx->cand_c, ctx->cand_n, ctx->cand_ref, ctx->cand_px);
+        ctx->launches++;
+        MVS_CUDA_CHECK(cudaGetLastError());
+    }
+    ctx->n_cand = M;
+    *n_candidates = M;
+    return MVS_OK;
+}
+
+extern "C" int mvs_round_score(mvs_ctx* ctx, const void* frontier, int64_t begin, int64_t end, double min_ncc, int wid,
+                               int bound, double scale, void* records, int64_t capacity, int64_t* n_out, void* stream) {
+    if (!ctx || !ctx->d_cells) { mvs_set_error("mvs_round_score: cell table not initialised"); return MVS_ERR_STATE; }
+    if (begin < 0 || end < begin || end > ctx->n_cand || !n_out || capacity < 0 || (end > begin && (!records || !frontier))) {
+        mvs_set_error("mvs_round_score: bad shard [%lld, %lld) of %lld candidates", (long long)begin, (long long)end,
+                      (long long)ctx->n_cand);
+        return MVS_ERR_ARG;
+    }
+    MVS_CUDA_CHECK(cudaSetDevice(ctx->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t n = end - begin;
+    if (n == 0) {
+        MVS_CUDA_CHECK(cudaMemsetAsync(n_out, 0, sizeof(int64_t), s));
+        return MVS_OK;
+    }
+    const size_t mw = (size_t)((ctx->V + 63) / 64);
+    int rc = mvs_launch_score_refexact(ctx, n, ctx->cand_c + 3 * begin, ctx->cand_ref + begin, min_ncc, wid,
+                                       ctx->cand_vis + mw * begin, ctx->cand_avg + begin, ctx->cand_count + begin,
+                                       ctx->cand_xy + 2 * begin, nullptr, s);
+    if (rc != MVS_OK) return rc;
+    expand_gate<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((const uint8_t*)frontier, rec_bytes_of(ctx), begin, end,
+                                                           ctx->cand_parent, ctx->cand_c, ctx->cand_n, 0.05 / scale,
+                                                           ctx->cand_gate);
+    ctx->launches++;
+    MVS_CUDA_CHECK(cudaGetLastError());
+    return mvs_launch_compact(ctx, n, 0, ctx->cand_c + 3 * begin, ctx->cand_n + 3 * begin, ctx->cand_ref + begin,
+                              ctx->cand_vis + mw * begin, ctx->cand_avg + begin, ctx->cand_count + begin,
+                              ctx->cand_xy + 2 * begin, ctx->cand_gate + begin, bound, records, capacity, n_out,
+                              ctx->cand_slot + begin, ctx->cand_px + 2 * begin, s);
+}
+
+extern "C" int mvs_round_commit(mvs_ctx* ctx, const void* records, int64_t n, void* next_frontier, int64_t* n_next,
+                                void* stream) {
+    if (!ctx || !ctx->d_cells) { mvs_set_error("mvs_round_commit: cell table not initialised"); return MVS_ERR_STATE; }
+    if (n < 0 || !n_next || (n > 0 && !records)) { mvs_set_error("mvs_round_commit: bad argument"); return MVS_ERR_ARG; }
+    MVS_CUDA_CHECK(cudaSetDevice(ctx->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n == 0) {
+        MVS_CUDA_CHECK(cudaMemsetAsync(n_next, 0, sizeof(int64_t), s));
+        return MVS_OK;
+    }
+    int rc;
+    if ((rc = mvs_ensure((void**)&ctx->d_counts, &ctx->counts_bytes, sizeof(int32_t) * n, "commit flags")) != MVS_OK) return rc;
+    if ((rc = mvs_ensure((void**)&ctx->d_scan, &ctx->scan_bytes, sizeof(int64_t) * ((n + 1023) / 1024 + 2), "scan")) != MVS_OK) return rc;
+    const int rb = rec_bytes_of(ctx);
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    commit_flags<<<blocks, 256, 0, s>>>((const uint8_t*)records, n, rb, ctx->d_counts);
+    if ((rc = mvs_exclusive_scan_i32(ctx->d_counts, n, ctx->d_scan, n_next, s)) != MVS_OK) return rc;
+    commit_apply<<<blocks, 256, 0, s>>>((const uint8_t*)records, n, rb, ctx->d_counts, n_next, (uint8_t*)next_frontier, ctx->V,
+                                       ctx->cell_size, ctx->wc, ctx->hc, ctx->d_cells);
+    ctx->launches += 5;
+    MVS_CUDA_CHECK(cudaGetLastError());
+    return MVS_OK;
+}
+
+extern "C" int mvs_round_candidates(mvs_ctx* ctx, int64_t* slot, int64_t* parent, double* c, double* nrm, int32_t* ref) {
+    if (!ctx) { mvs_set_error("null context"); return MVS_ERR_ARG; }
+    MVS_CUDA_CHECK(cudaSetDevice(ctx->device));
+    MVS_CUDA_CHECK(cudaDeviceSynchronize());
+    const int64_t M = ctx->n_cand;
+    if (M == 0) return MVS_OK;
+    if (slot) MVS_CUDA_CHECK(cudaMemcpy(slot, ctx->cand_slot, sizeof(int64_t) * M, cudaMemcpyDeviceToHost));
+    if (parent) MVS_CUDA_CHECK(cudaMemcpy(parent, ctx->cand_parent, sizeof(int64_t) * M, cudaMemcpyDeviceToHost));
+    if (c) MVS_CUDA_CHECK(cudaMemcpy(c, ctx->cand_c, sizeof(double) * 3 * M, cudaMemcpyDeviceToHost));
+    if (nrm) MVS_CUDA_CHECK(cudaMemcpy(nrm, ctx->cand_n, sizeof(double) * 3 * M, cudaMemcpyDeviceToHost));
+    if (ref) MVS_CUDA_CHECK(cudaMemcpy(ref, ctx->cand_ref, sizeof(int32_t) * M, cudaMemcpyDeviceToHost));
+    return MVS_OK;
+}

@@ -223,6 +223,11 @@ extern "C" int mvs_destroy(mvs_ctx* ctx) {
     if (ctx->d_geom) cudaFree(ctx->d_geom);
     if (ctx->d_stage) cudaFree(ctx->d_stage);
     if (ctx->d_tiles) cudaFree(ctx->d_tiles);
+    void* bufs[] = {ctx->d_cells, ctx->d_claim, ctx->d_counts, ctx->d_scan, ctx->cand_slot, ctx->cand_parent, ctx->cand_c,
+                    ctx->cand_n, ctx->cand_ref, ctx->cand_px, ctx->cand_vis, ctx->cand_avg, ctx->cand_count, ctx->cand_xy,
+                    ctx->cand_gate};
+    for (void* b : bufs)
+        if (b) cudaFree(b);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     free(ctx->h_rrt);
     free(ctx->h_centres);
@@ -323,5 +328,5 @@ extern "C" int mvs_compact_accepted(mvs_ctx* ctx, int64_t N, int64_t index_base,
     }
     MVS_CUDA_CHECK(cudaSetDevice(ctx->device));
     return mvs_launch_compact(ctx, N, index_base, c, nrm, ref, vis_mask, avg, count, xy, gate, bound, records, capacity,
-                              n_out, (cudaStream_t)stream);
+                              n_out, nullptr, nullptr, (cudaStream_t)stream);
 }

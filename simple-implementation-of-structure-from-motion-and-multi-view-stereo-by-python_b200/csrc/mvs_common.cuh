@@ -44,6 +44,30 @@ struct mvs_ctx {
     // compaction scratch
     int32_t* d_tiles;
     size_t tile_bytes;
+    // cell table (CellTable, MVS2.py:80-120) and round state
+    int cell_size, wc, hc;
+    uint8_t* d_cells;                 // [V, wc, hc], 1 = vacant
+    size_t cells_bytes;
+    unsigned long long* d_claim;      // [V, wc, hc] epoch-tagged slot claims
+    size_t claim_bytes;
+    unsigned epoch;
+    int32_t* d_counts;
+    size_t counts_bytes;
+    int64_t* d_scan;
+    size_t scan_bytes;
+    int64_t n_cand;
+    int64_t* cand_slot;
+    int64_t* cand_parent;
+    double* cand_c;
+    double* cand_n;
+    int32_t* cand_ref;
+    int32_t* cand_px;
+    uint64_t* cand_vis;
+    double* cand_avg;
+    int32_t* cand_count;
+    double* cand_xy;
+    uint8_t* cand_gate;
+    size_t cand_cap[11];
 };
 
 void mvs_set_error(const char* fmt, ...);
@@ -64,4 +88,5 @@ int mvs_launch_score_refexact(mvs_ctx* ctx, int64_t N, const double* c, const in
                               uint64_t* vis, double* avg, int32_t* count, double* xy, float* ncc, cudaStream_t s);
 int mvs_launch_compact(mvs_ctx* ctx, int64_t N, int64_t index_base, const double* c, const double* nrm, const int32_t* ref,
                        const uint64_t* vis, const double* avg, const int32_t* count, const double* xy, const uint8_t* gate,
-                       int bound, void* records, int64_t capacity, int64_t* d_n_out, cudaStream_t s);
+                       int bound, void* records, int64_t capacity, int64_t* d_n_out, const int64_t* index_arr,
+                       const int32_t* px, cudaStream_t s);

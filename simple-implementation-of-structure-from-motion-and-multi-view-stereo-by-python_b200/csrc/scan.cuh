@@ -1,0 +1,12 @@
+// Device-wide exclusive scan of an int32 array (three small launches), shared by the
+// compaction and expansion kernels.  Counts are small (<= a few per element), totals fit
+// int64.
+#pragma once
+#include "mvs_common.cuh"
+
+// in place: a[0..n) -> exclusive prefix sums; *total (device int64) = sum.  `tile_scratch`
+// must hold ceil(n/1024) int64 values.
+int mvs_exclusive_scan_i32(int32_t* a, int64_t n, int64_t* tile_scratch, int64_t* total, cudaStream_t s);
+
+// grow-on-demand device buffer
+int mvs_ensure(void** p, size_t* cap, size_t bytes, const char* what);

@@ -1,0 +1,152 @@
+"""Round-synchronous patch expansion (the reference's patch_expansion, MVS2.py:308-404,
+restructured): every round expands the whole frontier on the device, scores this GPU's
+shard of the candidates, exchanges the accepted patch records with ONE all-gather and
+commits them identically on every GPU, so the result does not depend on the GPU count.
+
+The driver is host-side plumbing over a backend:
+  DeviceBackend -- the C ABI (mvs_round_generate / mvs_round_score / mvs_round_commit);
+                   the only backend the product uses.  No CPU implementation exists here.
+Tests inject their own backend to exercise the sharding / gather logic without a GPU.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .context import MvsError, _check
+from .records import rec_dtype
+
+
+class DeviceBackend:
+    def __init__(self, ctx, cell_size=2, scale=1.0, bound=3, min_ncc=0.7, wid=5, table=None):
+        import torch
+        self.torch = torch
+        self.ctx = ctx
+        self.lib = _lib.load()
+        self.scale, self.bound, self.min_ncc, self.wid = float(scale), int(bound), float(min_ncc), int(wid)
+        self.rec_bytes = self.lib.mvs_record_bytes(ctx._h)
+        self.device = torch.device("cuda", ctx.device)
+        tab = None
+        if table is not None:
+            tab = np.ascontiguousarray(np.asarray(table, dtype=np.uint8))
+        _check(self.lib.mvs_cells_init(ctx._h, int(cell_size), C.c_void_p(tab.ctypes.data) if tab is not None else None),
+               "mvs_cells_init")
+        cs, wc, hc = C.c_int(), C.c_int(), C.c_int()
+        _check(self.lib.mvs_cells_shape(ctx._h, C.byref(cs), C.byref(wc), C.byref(hc)), "mvs_cells_shape")
+        self.cell_size, self.wc, self.hc = cs.value, wc.value, hc.value
+        self._n = torch.zeros(1, dtype=torch.int64, device=self.device)
+
+    def _stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def to_device(self, records_np):
+        t = self.torch
+        raw = np.ascontiguousarray(records_np).view(np.uint8).reshape(len(records_np), self.rec_bytes)
+        return t.from_numpy(raw.copy()).to(self.device)
+
+    def to_host(self, records_dev):
+        return records_dev.cpu().numpy().reshape(-1).view(rec_dtype(self.ctx.V))
+
+    def empty(self, n):
+        return self.torch.empty((n, self.rec_bytes), dtype=self.torch.uint8, device=self.device)
+
+    def fill(self, records_dev):
+        _check(self.lib.mvs_cells_fill(self.ctx._h, C.c_void_p(records_dev.data_ptr()), records_dev.shape[0], self._stream()),
+               "mvs_cells_fill")
+
+    def table(self):
+        out = np.empty((self.ctx.V, self.wc, self.hc), dtype=np.uint8)
+        _check(self.lib.mvs_cells_download(self.ctx._h, C.c_void_p(out.ctypes.data)), "mvs_cells_download")
+        return out.astype(bool)
+
+    def generate(self, frontier):
+        m = C.c_int64(0)
+        _check(self.lib.mvs_round_generate(self.ctx._h, C.c_void_p(frontier.data_ptr()), frontier.shape[0], C.byref(m),
+                                           self._stream()), "mvs_round_generate")
+        return int(m.value)
+
+    def candidates(self, M):
+        out = dict(slot=np.zeros(M, np.int64), parent=np.zeros(M, np.int64), c=np.zeros((M, 3)), n=np.zeros((M, 3)),
+                   ref=np.zeros(M, np.int32))
+        p = lambda a: C.c_void_p(a.ctypes.data)
+        _check(self.lib.mvs_round_candidates(self.ctx._h, p(out["slot"]), p(out["parent"]), p(out["c"]), p(out["n"]),
+                                             p(out["ref"])), "mvs_round_candidates")
+        return out
+
+    def score(self, frontier, begin, end):
+        cap = max(end - begin, 1)
+        recs = self.empty(cap)
+        _check(self.lib.mvs_round_score(self.ctx._h, C.c_void_p(frontier.data_ptr()), begin, end, self.min_ncc, self.wid,
+                                        self.bound, self.scale, C.c_void_p(recs.data_ptr()), cap,
+                                        C.c_void_p(self._n.data_ptr()), self._stream()), "mvs_round_score")
+        return recs, self._n
+
+    def commit(self, records):
+        n = records.shape[0]
+        nxt = self.empty(max(n, 1))
+        _check(self.lib.mvs_round_commit(self.ctx._h, C.c_void_p(records.data_ptr()) if n else None, n,
+                                         C.c_void_p(nxt.data_ptr()), C.c_void_p(self._n.data_ptr()), self._stream()),
+               "mvs_round_commit")
+        return nxt[: int(self._n.item())]
+
+
+def shard_bounds(M, rank, world):
+    """Block partition of the candidate list by global candidate index."""
+    return (M * rank) // world, (M * (rank + 1)) // world
+
+
+class RoundDriver:
+    """Runs rounds over a backend; with ``world > 1`` candidates are sharded by index and the
+    accepted records all-gathered (torch.distributed: NCCL on GPUs, gloo in CPU tests)."""
+
+    def __init__(self, backend, rank=0, world=1, group=None):
+        self.b = backend
+        self.rank, self.world, self.group = rank, world, group
+        self.stats = []
+
+    def _gather(self, recs, n_local):
+        import torch
+        import torch.distributed as dist
+        counts = torch.zeros(self.world, dtype=torch.int64, device=recs.device)
+        dist.all_gather_into_tensor(counts, n_local.reshape(1).to(torch.int64), group=self.group)
+        counts_h = counts.cpu().tolist()                          # one host sync per round: payload size
+        mx = max(max(counts_h), 1)
+        send = recs[:mx]
+        if send.shape[0] < mx:                                    # shard smaller than the largest accepted count
+            pad = torch.zeros((mx - send.shape[0], recs.shape[1]), dtype=recs.dtype, device=recs.device)
+            send = torch.cat([send, pad])
+        out = torch.empty((self.world * mx, recs.shape[1]), dtype=recs.dtype, device=recs.device)
+        dist.all_gather_into_tensor(out, send.contiguous(), group=self.group)
+        out = out.view(self.world, mx, recs.shape[1])
+        return torch.cat([out[r, :counts_h[r]] for r in range(self.world)]), counts_h
+
+    def round(self, frontier):
+        M = self.b.generate(frontier)
+        begin, end = shard_bounds(M, self.rank, self.world)
+        recs, n_local = self.b.score(frontier, begin, end)
+        if self.world > 1:
+            allrecs, counts = self._gather(recs, n_local)
+        else:
+            allrecs = recs[: int(n_local.item())]
+            counts = [allrecs.shape[0]]
+        nxt = self.b.commit(allrecs)
+        self.stats.append(dict(frontier=int(frontier.shape[0]), candidates=M, shard=(begin, end), passed=int(sum(counts)),
+                               accepted=int(nxt.shape[0])))
+        return nxt
+
+    def run(self, seeds, max_rounds=1000, max_patches=None):
+        """seeds: device record tensor (already filled into the table by the caller).  Returns
+        the list of per-round accepted record tensors."""
+        frontier = seeds
+        accepted = []
+        total = 0
+        for _ in range(max_rounds):
+            if frontier.shape[0] == 0:
+                break
+            frontier = self.round(frontier)
+            if frontier.shape[0]:
+                accepted.append(frontier)
+                total += frontier.shape[0]
+            if max_patches is not None and total >= max_patches:
+                break
+        return accepted

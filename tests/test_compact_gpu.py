@@ -7,7 +7,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 REC = np.dtype([("c", "<f8", 3), ("n", "<f8", 3), ("xy", "<f8", 2), ("avg", "<f8"), ("ref", "<i4"), ("count", "<i4"),
-                ("index", "<i8"), ("vis", "<u8", 1)])
+                ("index", "<i8"), ("px", "<i4", 2), ("vis", "<u8", 1)])
 
 
 @pytest.mark.parametrize("N", [0, 1, 1023, 1024, 1025, 50000])
