@@ -196,6 +196,16 @@ int mvs_round_commit(mvs_ctx* ctx, const void* records, int64_t n, void* next_fr
  * NULL; HOST pointers.  slot [M] int64, parent [M] int64, c [M,3], nrm [M,3], ref [M] int32. */
 int mvs_round_candidates(mvs_ctx* ctx, int64_t* slot, int64_t* parent, double* c, double* nrm, int32_t* ref);
 
+/*
+ * NCC of M descriptor pairs.
+ * Replaces: ctNcc(desc1, desc2) (MVS2.py:39-43) for uint8 descriptors of length n:
+ * out[m] = sum(z(a_m) * z(b_m)) / (n - 1) with population-std z-scores, i.e. n/(n-1) times the
+ * Pearson correlation; NaN when a descriptor has zero variance.  No context needed.
+ *   a, b [M,n] uint8, out [M] float64; host or device pointers (on_device)
+ */
+int mvs_ncc_pairs(int device, int64_t M, int n, const uint8_t* a, const uint8_t* b, double* out, int on_device,
+                  void* stream);
+
 /* Number of kernels this library has launched on ctx since creation (for bench.py's
  * gpu_launches claim). */
 int64_t mvs_launch_count(const mvs_ctx* ctx);

@@ -30,6 +30,7 @@ SYMBOLS = {
                                   _P, _P]),
     "mvs_round_commit": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P]),
     "mvs_round_candidates": (C.c_int, [_P, _P, _P, _P, _P, _P]),
+    "mvs_ncc_pairs": (C.c_int, [C.c_int, C.c_int64, C.c_int, _P, _P, _P, C.c_int, _P]),
     "mvs_compact_accepted": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, _P, C.c_int64,
                                        _P, _P]),
 }

@@ -15,8 +15,10 @@ MODE_REFEXACT = 0
 MODE_PMVS = 1
 
 
-class MvsError(RuntimeError):
-    pass
+class MvsError(Exception):
+    """Raised for every failure of the device path.  Deliberately NOT a RuntimeError: the
+    reference's main.py swallows RuntimeError (main.py:43-46) and a missing GPU or library
+    must stop the program loudly instead of printing one word."""
 
 
 def _check(rc, what):
