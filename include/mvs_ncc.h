@@ -68,7 +68,8 @@ int mvs_create(mvs_ctx** out, int device, int V, int H, int W, const uint8_t* rg
 
 int mvs_destroy(mvs_ctx* ctx);
 
-/* Geometry of the resident stack: views, rows, cols, row pitch in bytes. */
+/* Geometry of the resident stack: views, rows, cols, and the byte pitch of one image row of
+ * the view-interleaved layout u8 [H][G][Vp][4] (all views of a row are adjacent). */
 int mvs_get_info(const mvs_ctx* ctx, int* V, int* H, int* W, int64_t* pitch);
 
 /* Copy the resident gray stack back to the host as a dense [V,H,W] uint8 array. */

@@ -129,11 +129,14 @@ extern "C" int mvs_create(mvs_ctx** out, int device, int V, int H, int W, const 
     ctx->V = V;
     ctx->H = H;
     ctx->W = W;
-    ctx->pitch = ((int64_t)W + 127) / 128 * 128;
-    ctx->vstride = ctx->pitch * H;
+    ctx->Vp = (V + 3) / 4 * 4;
+    ctx->Q = ctx->Vp / 4;
+    ctx->G = (W + 3) / 4 + MVS_GROUP_PAD;
+    ctx->gstride = 4 * (int64_t)ctx->Vp;
+    ctx->rowpitch = ctx->G * ctx->gstride;
     ctx->sm_count = prop.multiProcessorCount;
     int rc = MVS_OK;
-    const size_t gray_bytes = (size_t)ctx->vstride * V + 256;
+    const size_t gray_bytes = (size_t)ctx->rowpitch * H + 256;
     const size_t rgb_bytes = (size_t)V * H * W * 3;
     uint8_t* d_rgb = nullptr;
     CamProj* hp = (CamProj*)malloc(sizeof(CamProj) * V);
@@ -240,15 +243,20 @@ extern "C" int mvs_get_info(const mvs_ctx* ctx, int* V, int* H, int* W, int64_t*
     if (V) *V = ctx->V;
     if (H) *H = ctx->H;
     if (W) *W = ctx->W;
-    if (pitch) *pitch = ctx->pitch;
+    if (pitch) *pitch = ctx->rowpitch;
     return MVS_OK;
 }
 
 extern "C" int mvs_download_gray(mvs_ctx* ctx, uint8_t* out_host) {
     if (!ctx || !out_host) { mvs_set_error("mvs_download_gray: null argument"); return MVS_ERR_ARG; }
     MVS_CUDA_CHECK(cudaSetDevice(ctx->device));
-    MVS_CUDA_CHECK(cudaMemcpy2D(out_host, ctx->W, ctx->d_gray, ctx->pitch, ctx->W, (size_t)ctx->V * ctx->H,
-                                cudaMemcpyDeviceToHost));
+    const size_t bytes = (size_t)ctx->V * ctx->H * ctx->W;
+    int rc = ensure_stage(ctx, bytes);
+    if (rc != MVS_OK) return rc;
+    rc = mvs_launch_unpack_gray(ctx, (uint8_t*)ctx->d_stage, ctx->own_stream);
+    if (rc != MVS_OK) return rc;
+    MVS_CUDA_CHECK(cudaMemcpyAsync(out_host, ctx->d_stage, bytes, cudaMemcpyDeviceToHost, ctx->own_stream));
+    MVS_CUDA_CHECK(cudaStreamSynchronize(ctx->own_stream));
     return MVS_OK;
 }
 

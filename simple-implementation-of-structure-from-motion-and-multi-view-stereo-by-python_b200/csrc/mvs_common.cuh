@@ -8,6 +8,7 @@
 #include "mvs_ncc.h"
 
 #define MVS_ABI_VERSION 1
+#define MVS_GROUP_PAD 8
 
 // One view's projection parameters as the scorer reads them (128 B, fp64).
 // r = Rodrigues round trip of the file rotation (utils.py:242-243).
@@ -28,9 +29,17 @@ struct __align__(16) CamGeom {
 struct mvs_ctx {
     int device;
     int V, H, W;
-    int64_t pitch;        // bytes per gray row (multiple of 128)
-    int64_t vstride;      // bytes per gray view = H * pitch
-    uint8_t* d_gray;      // [V, H, pitch] + 256 B tail pad
+    // Resident gray stack, VIEW-INTERLEAVED: u8 [H][G][Vp][4] -- four consecutive pixels of
+    // one view form a 32-bit word, the words of all views for the same four pixels are
+    // adjacent.  Byte (v, row, col) lives at row*rowpitch + (col>>2)*gstride + 4*v + (col&3).
+    // Mode A samples every view at the SAME (row, col) (MVS2.py:68), so one window row of all
+    // views is a single contiguous run of <= NG*gstride bytes.
+    int Vp;               // V rounded up to a multiple of 4 (padding views are zero)
+    int Q;                // Vp / 4: 16-byte quads (4 views x 4 pixels) per pixel group
+    int G;                // pixel groups per row, ceil(W/4) + MVS_GROUP_PAD zero groups
+    int64_t gstride;      // bytes per pixel group = 4 * Vp
+    int64_t rowpitch;     // bytes per image row = G * gstride
+    uint8_t* d_gray;      // [H, G, Vp, 4] + 256 B tail pad
     CamProj* d_cam;       // [V]
     CamGeom* d_geom;      // [V]
     double* h_rrt;        // [V,9] host copy
@@ -84,6 +93,7 @@ void mvs_set_error(const char* fmt, ...);
 
 // kernels / launchers implemented in the .cu files
 int mvs_launch_gray(mvs_ctx* ctx, const uint8_t* d_rgb, cudaStream_t s);
+int mvs_launch_unpack_gray(mvs_ctx* ctx, uint8_t* d_planar, cudaStream_t s);
 int mvs_launch_score_refexact(mvs_ctx* ctx, int64_t N, const double* c, const int32_t* ref, double thr, int wid,
                               uint64_t* vis, double* avg, int32_t* count, double* xy, float* ncc, cudaStream_t s);
 int mvs_launch_compact(mvs_ctx* ctx, int64_t N, int64_t index_base, const double* c, const double* nrm, const int32_t* ref,
