@@ -207,6 +207,16 @@ int mvs_round_candidates(mvs_ctx* ctx, int64_t* slot, int64_t* parent, double* c
 int mvs_ncc_pairs(int device, int64_t M, int n, const uint8_t* a, const uint8_t* b, double* out, int on_device,
                   void* stream);
 
+/*
+ * Measurement hooks (bench.py): while enabled, every mvs_score_batch / mvs_round_score
+ * brackets its scoring kernel (K1 alone, without the projection/binning launches before
+ * it) with two CUDA events on the stream the kernel is launched on (a ring of the last 64
+ * launches).  mvs_profile_score_ms waits for those kernels and returns their MEAN duration
+ * in milliseconds and how many were averaged; mvs_profile_enable(ctx, 1) restarts the count.
+ */
+int mvs_profile_enable(mvs_ctx* ctx, int on);
+int mvs_profile_score_ms(mvs_ctx* ctx, float* mean_ms, int* n_kernels);
+
 /* Number of kernels this library has launched on ctx since creation (for bench.py's
  * gpu_launches claim). */
 int64_t mvs_launch_count(const mvs_ctx* ctx);

@@ -114,6 +114,17 @@ class MvsContext:
     def launch_count(self):
         return int(_lib.load().mvs_launch_count(self._h))
 
+    def profile(self, on=True):
+        """Bracket every scoring kernel with CUDA events on its launch stream."""
+        _check(_lib.load().mvs_profile_enable(self._h, 1 if on else 0), "mvs_profile_enable")
+
+    def score_kernel_ms(self):
+        """(mean ms, n) over the scoring kernels (K1 alone) launched since profile(True), at most
+        the last 64; waits for them to finish."""
+        ms, n = C.c_float(), C.c_int()
+        _check(_lib.load().mvs_profile_score_ms(self._h, C.byref(ms), C.byref(n)), "mvs_profile_score_ms")
+        return float(ms.value), int(n.value)
+
     # -- scoring ---------------------------------------------------------------------
     def score_host(self, c, ref, min_ncc=0.7, wid=5, nrm=None, mode=MODE_REFEXACT, want_ncc=False):
         """Host buffers in, host buffers out (copies + sync inside the call).

@@ -100,8 +100,8 @@ static int ensure_stage(mvs_ctx* ctx, size_t bytes) {
 
 extern "C" int mvs_create(mvs_ctx** out, int device, int V, int H, int W, const uint8_t* rgb, int rgb_on_device,
                           const double* K, const double* R, const double* Rrt, const double* t) {
-    if (!out || !rgb || !K || !R || !t || V < 1 || V > 1024 || H < 1 || W < 1) {
-        mvs_set_error("mvs_create: bad argument (need 1 <= V <= 1024, H, W >= 1, non-null rgb/K/R/t)");
+    if (!out || !rgb || !K || !R || !t || V < 1 || V > 1024 || H < 1 || W < 1 || H > 65535 || W > 65535) {
+        mvs_set_error("mvs_create: bad argument (need 1 <= V <= 1024, 1 <= H, W <= 65535, non-null rgb/K/R/t)");
         return MVS_ERR_ARG;
     }
     *out = nullptr;
@@ -135,6 +135,7 @@ extern "C" int mvs_create(mvs_ctx** out, int device, int V, int H, int W, const 
     ctx->gstride = 4 * (int64_t)ctx->Vp;
     ctx->rowpitch = ctx->G * ctx->gstride;
     ctx->sm_count = prop.multiProcessorCount;
+    ctx->maps_wid = -1;
     int rc = MVS_OK;
     const size_t gray_bytes = (size_t)ctx->rowpitch * H + 256;
     const size_t rgb_bytes = (size_t)V * H * W * 3;
@@ -226,11 +227,17 @@ extern "C" int mvs_destroy(mvs_ctx* ctx) {
     if (ctx->d_geom) cudaFree(ctx->d_geom);
     if (ctx->d_stage) cudaFree(ctx->d_stage);
     if (ctx->d_tiles) cudaFree(ctx->d_tiles);
+    void* more[] = {ctx->d_smap, ctx->d_vmap, ctx->d_bin_hist, ctx->d_bin_key, ctx->d_bin_rank, ctx->d_bin_order,
+                    ctx->d_bin_anchor, ctx->d_bin_sanchor, ctx->d_bin_scan};
+    for (void* b : more)
+        if (b) cudaFree(b);
     void* bufs[] = {ctx->d_cells, ctx->d_claim, ctx->d_counts, ctx->d_scan, ctx->cand_slot, ctx->cand_parent, ctx->cand_c,
                     ctx->cand_n, ctx->cand_ref, ctx->cand_px, ctx->cand_vis, ctx->cand_avg, ctx->cand_count, ctx->cand_xy,
                     ctx->cand_gate};
     for (void* b : bufs)
         if (b) cudaFree(b);
+    for (int i = 0; i < 2 * MVS_PROF_RING; ++i)
+        if (ctx->prof_ev[i]) cudaEventDestroy(ctx->prof_ev[i]);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     free(ctx->h_rrt);
     free(ctx->h_centres);
@@ -264,6 +271,38 @@ extern "C" int mvs_get_cameras(const mvs_ctx* ctx, double* Rrt_host, double* cen
     if (!ctx) { mvs_set_error("null context"); return MVS_ERR_ARG; }
     if (Rrt_host) memcpy(Rrt_host, ctx->h_rrt, sizeof(double) * 9 * ctx->V);
     if (centres_host) memcpy(centres_host, ctx->h_centres, sizeof(double) * 3 * ctx->V);
+    return MVS_OK;
+}
+
+extern "C" int mvs_profile_enable(mvs_ctx* ctx, int on) {
+    if (!ctx) { mvs_set_error("null context"); return MVS_ERR_ARG; }
+    MVS_CUDA_CHECK(cudaSetDevice(ctx->device));
+    if (on && !ctx->prof_ev[0]) {
+        for (int i = 0; i < 2 * MVS_PROF_RING; ++i) MVS_CUDA_CHECK(cudaEventCreate(&ctx->prof_ev[i]));
+    }
+    ctx->profile = on ? 1 : 0;
+    if (on) ctx->prof_n = 0;
+    return MVS_OK;
+}
+
+extern "C" int mvs_profile_score_ms(mvs_ctx* ctx, float* mean_ms, int* n_kernels) {
+    if (!ctx || !mean_ms) { mvs_set_error("mvs_profile_score_ms: null argument"); return MVS_ERR_ARG; }
+    if (!ctx->prof_ev[0] || ctx->prof_n == 0) {
+        mvs_set_error("mvs_profile_score_ms: no scoring kernel has been timed (call mvs_profile_enable first)");
+        return MVS_ERR_STATE;
+    }
+    MVS_CUDA_CHECK(cudaSetDevice(ctx->device));
+    const int n = (int)(ctx->prof_n < MVS_PROF_RING ? ctx->prof_n : MVS_PROF_RING);
+    double sum = 0.0;
+    for (int k = 0; k < n; ++k) {
+        const int slot = (int)((ctx->prof_n - 1 - k) % MVS_PROF_RING);
+        float ms = 0.f;
+        MVS_CUDA_CHECK(cudaEventSynchronize(ctx->prof_ev[2 * slot + 1]));
+        MVS_CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->prof_ev[2 * slot], ctx->prof_ev[2 * slot + 1]));
+        sum += ms;
+    }
+    *mean_ms = (float)(sum / n);
+    if (n_kernels) *n_kernels = n;
     return MVS_OK;
 }
 

@@ -9,6 +9,10 @@
 
 #define MVS_ABI_VERSION 1
 #define MVS_GROUP_PAD 8
+#define MVS_PROF_RING 64
+#define MVS_ANCHOR_INVALID 0xffffffffu
+#define MVS_BIN_SHIFT 3          // anchor tiles of 8x8 pixels
+#define MVS_SORT_MIN 8192        // batches smaller than this are scored in input order
 
 // One view's projection parameters as the scorer reads them (128 B, fp64).
 // r = Rodrigues round trip of the file rotation (utils.py:242-243).
@@ -40,6 +44,26 @@ struct mvs_ctx {
     int64_t gstride;      // bytes per pixel group = 4 * Vp
     int64_t rowpitch;     // bytes per image row = G * gstride
     uint8_t* d_gray;      // [H, G, Vp, 4] + 256 B tail pad
+    // Per-anchor window sums of every view for half window maps_wid (built on first use):
+    //   smap u16 [H][W][Vp] = sum(w),  vmap u32 [H][W][Vp] = n*sum(w*w) - sum(w)^2  (exact)
+    uint16_t* d_smap;
+    uint32_t* d_vmap;
+    size_t smap_bytes, vmap_bytes;
+    int maps_wid;
+    // spatial binning scratch (bin.cu): hypotheses ordered by 8x8-pixel anchor tile
+    int32_t* d_bin_hist;   // [tiles + 2]
+    int32_t* d_bin_key;    // [N]
+    int32_t* d_bin_rank;   // [N]
+    int32_t* d_bin_order;  // [N] hypothesis index per sorted position
+    uint32_t* d_bin_anchor;   // [N] row<<16 | col per hypothesis (MVS_ANCHOR_INVALID = rejected)
+    uint32_t* d_bin_sanchor;  // [N] the same per sorted position
+    int64_t* d_bin_scan;
+    size_t bin_hist_bytes, bin_key_bytes, bin_rank_bytes, bin_order_bytes, bin_anchor_bytes, bin_sanchor_bytes,
+        bin_scan_bytes;
+    // optional CUDA-event bracket around the scoring kernel (mvs_profile_enable)
+    int profile;
+    cudaEvent_t prof_ev[2 * MVS_PROF_RING];
+    int64_t prof_n;       // scoring kernels bracketed since mvs_profile_enable(1)
     CamProj* d_cam;       // [V]
     CamGeom* d_geom;      // [V]
     double* h_rrt;        // [V,9] host copy
@@ -96,6 +120,11 @@ int mvs_launch_gray(mvs_ctx* ctx, const uint8_t* d_rgb, cudaStream_t s);
 int mvs_launch_unpack_gray(mvs_ctx* ctx, uint8_t* d_planar, cudaStream_t s);
 int mvs_launch_score_refexact(mvs_ctx* ctx, int64_t N, const double* c, const int32_t* ref, double thr, int wid,
                               uint64_t* vis, double* avg, int32_t* count, double* xy, float* ncc, cudaStream_t s);
+int mvs_build_window_maps(mvs_ctx* ctx, int wid, cudaStream_t s);
+// project + validate every hypothesis (writes xy and, for rejected ones, the empty result),
+// optionally order them by anchor tile; leaves anchors / order in ctx->d_bin_*
+int mvs_bin_hypotheses(mvs_ctx* ctx, int64_t N, const double* c, const int32_t* ref, int wid, bool sort, uint64_t* vis,
+                       double* avg, int32_t* count, double* xy, float* ncc, cudaStream_t s);
 int mvs_launch_compact(mvs_ctx* ctx, int64_t N, int64_t index_base, const double* c, const double* nrm, const int32_t* ref,
                        const uint64_t* vis, const double* avg, const int32_t* count, const double* xy, const uint8_t* gate,
                        int bound, void* records, int64_t capacity, int64_t* d_n_out, const int64_t* index_arr,

@@ -12,14 +12,18 @@
 // NG * 4*Vp bytes, 16-byte aligned.  A hypothesis is owned by LPH lanes (LPH = 4, 8, 16
 // or 32, the power of two >= Vp/4), 32/LPH hypotheses per warp.  Lane q owns the four
 // views 4q..4q+3: per window row and pixel group it issues ONE 16-byte load (4 views x 4
-// pixels), and per 32-bit word three dp4a give sum(w), sum(w*w), sum(w*ref) on packed
-// u8 -- exact in int32.  There is NO cross-lane reduction of the per-view sums: each
-// lane finishes its own four views, the ratio is taken in fp64 in the oracle's
-// operation order so that the strict threshold test agrees bit for bit.  The reference
-// window (K x NG masked words) is staged in shared memory once per hypothesis and read
-// back as one broadcast LDS.128 per window row.  Tensor cores are not used: this is a
-// gather-bound integer reduction with no dense contraction.
-#include "mvs_common.cuh"
+// pixels) and four dp4a against the masked reference word give sum(w*ref) on packed u8,
+// exact in int32.  sum(w) and n*sum(w^2)-sum(w)^2 of every view do not depend on the
+// reference view: they are box sums, computed once per (wid) into two resident maps
+// (K0b) and read back with one 8-byte and one 16-byte load per lane.  There is NO
+// cross-lane reduction of per-view sums: each lane finishes its own four views in fp64.
+// The reference window (K x NG masked words) is staged in shared memory once per
+// hypothesis and read back as one broadcast LDS.128 per window row.  Hypotheses arrive
+// ordered by anchor tile (bin.cu), so neighbouring lane groups hit the same L1 lines.
+// Tensor cores are not used: this is a gather-bound integer reduction with no dense
+// contraction.
+#include "project.cuh"
+#include "scan.cuh"
 
 #define FULL 0xffffffffu
 
@@ -99,56 +103,84 @@ int mvs_launch_unpack_gray(mvs_ctx* ctx, uint8_t* d_planar, cudaStream_t s) {
 }
 
 // ---------------------------------------------------------------------------------
-// Projection, bit-compatible with cv2.projectPoints as called by utils.py:241-244:
-//   X = (r0*c0 + r1*c1 + r2*c2) + t  (left to right, no FMA contraction),
-//   z = z ? 1/z : 1;  x = (X*z)*fx + cx.
+// K0b: per-anchor window sums of every view (box sums, independent of the reference
+// view): smap = sum(w), vmap = n*sum(w^2) - sum(w)^2, for every anchor that passes the
+// bounds rule of HarrisFeatures.py:128.  One thread = one anchor x one view quad.
 // ---------------------------------------------------------------------------------
-__device__ __forceinline__ void project_ref(const CamProj& cam, double c0, double c1, double c2, double& x, double& y) {
-    const double X =
-        __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(cam.r[0], c0), __dmul_rn(cam.r[1], c1)), __dmul_rn(cam.r[2], c2)), cam.t[0]);
-    const double Y =
-        __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(cam.r[3], c0), __dmul_rn(cam.r[4], c1)), __dmul_rn(cam.r[5], c2)), cam.t[1]);
-    const double Z =
-        __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(cam.r[6], c0), __dmul_rn(cam.r[7], c1)), __dmul_rn(cam.r[8], c2)), cam.t[2]);
-    const double iz = (Z != 0.0) ? __ddiv_rn(1.0, Z) : 1.0;
-    x = __dadd_rn(__dmul_rn(__dmul_rn(X, iz), cam.fx), cam.cx);
-    y = __dadd_rn(__dmul_rn(__dmul_rn(Y, iz), cam.fy), cam.cy);
-}
-
-// int() truncation toward zero + the asymmetric bounds rule of HarrisFeatures.py:128.
-// Non-finite projections are rejected (the reference would raise inside int()).
-__device__ __forceinline__ bool window_anchor(double x, double y, int H, int W, int wid, int& row, int& col) {
-    if (!(isfinite(x) && isfinite(y))) {
-        row = col = 0;
-        return false;
+template <int WID>
+__global__ void __launch_bounds__(256)
+    build_window_maps(const uint8_t* __restrict__ gray4, uint16_t* __restrict__ smap, uint32_t* __restrict__ vmap, int Vp,
+                      int Q, int H, int W, int64_t gstride, int64_t rowpitch) {
+    constexpr int K = 2 * WID + 1;
+    constexpr int NG = (K + 6) / 4;
+    constexpr uint32_t NPIX = K * K;
+    const int64_t total = (int64_t)H * W * Q;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int q = (int)(i % Q);
+        const int64_t px = i / Q;
+        const int col = (int)(px % W);
+        const int row = (int)(px / W);
+        if (!((row - WID >= 0) && (row + WID + 1 < H) && (col - WID > 0) && (col + WID + 1 < W))) continue;
+        const int o = (col - WID) & 3;
+        const uint8_t* pq = gray4 + (int64_t)(row - WID) * rowpitch + (int64_t)((col - WID) >> 2) * gstride + q * 16;
+        uint32_t S[4] = {0, 0, 0, 0}, SS[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            const uint32_t mg = group_mask(o, K, g);
+            if (mg == 0u) continue;
+#pragma unroll
+            for (int rr = 0; rr < K; ++rr) {
+                const uint4 w4 = __ldg(reinterpret_cast<const uint4*>(pq + rr * rowpitch + g * gstride));
+                const uint32_t w[4] = {w4.x & mg, w4.y & mg, w4.z & mg, w4.w & mg};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    S[k] = __dp4a(w[k], 0x01010101u, S[k]);
+                    SS[k] = __dp4a(w[k], w[k], SS[k]);
+                }
+            }
+        }
+        // n*SS and S*S are <= 225^2 * 255^2 < 2^32 and n*SS >= S*S: exact in u32
+        uint4 var;
+        var.x = NPIX * SS[0] - S[0] * S[0];
+        var.y = NPIX * SS[1] - S[1] * S[1];
+        var.z = NPIX * SS[2] - S[2] * S[2];
+        var.w = NPIX * SS[3] - S[3] * S[3];
+        uint2 s2;
+        s2.x = S[0] | (S[1] << 16);
+        s2.y = S[2] | (S[3] << 16);
+        *reinterpret_cast<uint4*>(vmap + px * Vp + 4 * q) = var;
+        *reinterpret_cast<uint2*>(smap + px * Vp + 4 * q) = s2;
     }
-    const double lim = 1073741824.0;
-    row = (int)fmin(fmax(y, -lim), lim);
-    col = (int)fmin(fmax(x, -lim), lim);
-    return (row - wid >= 0) && (row + wid + 1 < H) && (col - wid > 0) && (col + wid + 1 < W);
 }
 
-__device__ __forceinline__ int dp4a_u(uint32_t a, uint32_t b, int c) { return (int)__dp4a(a, b, (unsigned)c); }
-
-// Bytes of pixel group g (window-relative positions 4g..4g+3) that lie inside the
-// K-pixel run starting at offset o (0..3) of group 0.
-__device__ __forceinline__ uint32_t group_mask(int o, int K, int g) {
-    int lo = o - 4 * g;
-    lo = lo < 0 ? 0 : lo;
-    int hi = o + K - 1 - 4 * g;
-    hi = hi > 3 ? 3 : hi;
-    if (lo > hi) return 0u;
-    return (0xffffffffu << (8 * lo)) & (0xffffffffu >> (8 * (3 - hi)));
-}
-
-// Final ratio in fp64, same operation order as oracle/mode_a.py::score.  All integer
-// terms are exact: n*SS, S*S <= 225^2*255^2 need 64 bits at wid = 7.
-__device__ __forceinline__ double ncc_from_sums(int n, int S, int SS, int SAB, int Sr, long long var_r, bool& defined) {
-    const long long var_i = (long long)n * SS - (long long)S * S;
-    const long long num = (long long)n * SAB - (long long)S * Sr;
-    defined = (var_i != 0) && (var_r != 0);
-    const double den = (double)var_i * (double)var_r;
-    return ((double)num / sqrt(den)) * ((double)n / (double)(n - 1));
+int mvs_build_window_maps(mvs_ctx* ctx, int wid, cudaStream_t s) {
+    if (ctx->maps_wid == wid && ctx->d_smap && ctx->d_vmap) return MVS_OK;
+    const size_t n = (size_t)ctx->H * ctx->W * ctx->Vp;
+    int rc;
+    if ((rc = mvs_ensure((void**)&ctx->d_smap, &ctx->smap_bytes, n * sizeof(uint16_t) + 256, "window-sum map")) != MVS_OK ||
+        (rc = mvs_ensure((void**)&ctx->d_vmap, &ctx->vmap_bytes, n * sizeof(uint32_t) + 256, "window-variance map")) != MVS_OK)
+        return rc;
+    ctx->maps_wid = -1;
+    MVS_CUDA_CHECK(cudaMemsetAsync(ctx->d_smap, 0, n * sizeof(uint16_t), s));
+    MVS_CUDA_CHECK(cudaMemsetAsync(ctx->d_vmap, 0, n * sizeof(uint32_t), s));
+    const int64_t total = (int64_t)ctx->H * ctx->W * ctx->Q;
+    int64_t blocks = (total + 255) / 256;
+    const int64_t cap = (int64_t)ctx->sm_count * 32;
+    if (blocks > cap) blocks = cap;
+#define MVS_MAPS(WID_)                                                                                              \
+    case WID_:                                                                                                      \
+        build_window_maps<WID_><<<(int)blocks, 256, 0, s>>>(ctx->d_gray, ctx->d_smap, ctx->d_vmap, ctx->Vp, ctx->Q, \
+                                                            ctx->H, ctx->W, ctx->gstride, ctx->rowpitch);           \
+        break;
+    switch (wid) {
+        MVS_MAPS(1) MVS_MAPS(2) MVS_MAPS(3) MVS_MAPS(4) MVS_MAPS(5) MVS_MAPS(6) MVS_MAPS(7)
+        default: mvs_set_error("wid %d not supported (1..7)", wid); return MVS_ERR_ARG;
+    }
+#undef MVS_MAPS
+    ctx->launches++;
+    MVS_CUDA_CHECK(cudaGetLastError());
+    ctx->maps_wid = wid;
+    return MVS_OK;
 }
 
 template <int LPH>
@@ -160,20 +192,36 @@ __device__ __forceinline__ uint32_t hyp_mask(int sub) {
     }
 }
 
+// ncc = (num / sqrt(var_i * var_r)) * n/(n-1), oracle/mode_a.py::score operation order.
+// Fast path: num * rsqrt(den) * n/(n-1) is within a few ulp of that; only a value closer
+// than 1e-9 to the threshold is recomputed with the correctly rounded sqrt and division,
+// so the strict '>' decision is always the oracle's.
+__device__ __forceinline__ double ncc_ratio(double num, double var_i, double var_r, double cn, double thr) {
+    const double den = var_i * var_r;
+    double val = (num * rsqrt(den)) * cn;
+    if (__builtin_expect(fabs(val - thr) < 1e-9, 0)) val = (num / sqrt(den)) * cn;
+    return val;
+}
+
 // ---------------------------------------------------------------------------------
-// K1: LPH lanes per hypothesis, 32/LPH hypotheses per warp, grid-stride.
+// K1: LPH lanes per hypothesis, 32/LPH hypotheses per warp.  A CTA walks chunks of
+// CHUNK consecutive positions of the (tile-ordered) batch so that its lane groups share
+// L1 lines.  anchors[i] = row<<16|col of position i (MVS_ANCHOR_INVALID: rejected,
+// result already written by bin_project); order[i] = hypothesis index (NULL: identity).
 // ---------------------------------------------------------------------------------
 template <int WID, int LPH>
 __global__ void __launch_bounds__(256, 2)
-    ncc_score_gather(const uint8_t* __restrict__ gray4, const CamProj* __restrict__ cams, int V, int Q, int H, int W,
-                     int64_t gstride, int64_t rowpitch, int64_t N, const double* __restrict__ c,
+    ncc_score_gather(const uint8_t* __restrict__ gray4, const uint16_t* __restrict__ smap, const uint32_t* __restrict__ vmap,
+                     int V, int Vp, int Q, int W, int64_t gstride, int64_t rowpitch, int64_t N,
+                     const uint32_t* __restrict__ anchors, const int32_t* __restrict__ order,
                      const int32_t* __restrict__ ref, double thr, uint64_t* __restrict__ vis_out,
-                     double* __restrict__ avg_out, int32_t* __restrict__ count_out, double* __restrict__ xy_out,
-                     float* __restrict__ ncc_out) {
+                     double* __restrict__ avg_out, int32_t* __restrict__ count_out, float* __restrict__ ncc_out) {
     constexpr int K = 2 * WID + 1;
     constexpr int NG = (K + 6) / 4;            // pixel groups a K-pixel run at offset 0..3 can touch
     constexpr int NPIX = K * K;
     constexpr int HPW = 32 / LPH;
+    constexpr int ITERS = 8;
+    constexpr int CHUNK = 8 * HPW * ITERS;
     __shared__ __align__(16) uint32_t s_ref[8][HPW][K][NG];
 
     const int lane = threadIdx.x & 31;
@@ -181,168 +229,174 @@ __global__ void __launch_bounds__(256, 2)
     const int sub = lane / LPH;
     const int lih = lane % LPH;
     const uint32_t hmask = hyp_mask<LPH>(sub);
-    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int mask_words32 = 2 * ((V + 63) >> 6);          // 32-bit chunks per hypothesis in vis_out
     const int passes = (LPH == 32) ? (Q + 31) >> 5 : 1;
+    const double cn = (double)NPIX / (double)(NPIX - 1);
     uint32_t(*sref)[NG] = s_ref[wib][sub];
 
-    for (int64_t h0 = warp0 * HPW; h0 < N; h0 += nwarps * HPW) {
-        const int64_t h = h0 + sub;
-        if (h >= N) continue;                              // the whole lane group leaves together
-        const int r = __ldg(ref + h);
-        double x = nan(""), y = nan("");
-        int row = 0, col = 0;
-        bool valid = false;
-        if (r >= 0 && r < V) {
-            const double c0 = __ldg(c + 3 * h), c1 = __ldg(c + 3 * h + 1), c2 = __ldg(c + 3 * h + 2);
-            project_ref(cams[r], c0, c1, c2, x, y);
-            valid = window_anchor(x, y, H, W, WID, row, col);
-        }
-        if (lih == 0 && xy_out) {
-            xy_out[2 * h] = x;
-            xy_out[2 * h + 1] = y;
-        }
-        if (!valid) {                                      // getDescFeatures -> [None]: V = [], avg = 0
-            for (int w = lih; w < mask_words32; w += LPH) reinterpret_cast<uint32_t*>(vis_out)[h * mask_words32 + w] = 0u;
-            if (lih == 0) {
-                count_out[h] = 0;
-                if (avg_out) avg_out[h] = 0.0;
+    for (int64_t i0 = (int64_t)blockIdx.x * CHUNK; i0 < N; i0 += (int64_t)gridDim.x * CHUNK) {
+        for (int it = 0; it < ITERS; ++it) {
+            const int64_t i = i0 + (it * 8 + wib) * HPW + sub;
+            if (i >= N) continue;                          // the whole lane group leaves together
+            const uint32_t a = __ldg(anchors + i);
+            if (a == MVS_ANCHOR_INVALID) continue;
+            const int64_t h = order ? (int64_t)__ldg(order + i) : i;
+            const int r = __ldg(ref + h);
+            const int row = (int)(a >> 16), col = (int)(a & 0xffffu);
+            const int o = (col - WID) & 3;                 // offset of the window inside its first pixel group
+            const uint8_t* base = gray4 + (int64_t)(row - WID) * rowpitch + (int64_t)((col - WID) >> 2) * gstride;
+            const int64_t mi = ((int64_t)row * W + col) * Vp;
+            const int Sr = (int)__ldg(smap + mi + r);
+            const double var_r = (double)__ldg(vmap + mi + r);
+            // byte masks of the window inside each pixel group; empty groups re-read group 0
+            // (an L1 hit) against a zero reference word instead of branching
+            uint32_t m[NG];
+            int64_t goff[NG];
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                m[g] = group_mask(o, K, g);
+                goff[g] = m[g] ? g * gstride : 0;
             }
-            if (ncc_out)
-                for (int v = lih; v < V; v += LPH) ncc_out[h * V + v] = nanf("");
-            continue;
-        }
-        const int o = (col - WID) & 3;                     // offset of the window inside its first pixel group
-        const uint8_t* base = gray4 + (int64_t)(row - WID) * rowpitch + (int64_t)((col - WID) >> 2) * gstride;
-        uint32_t m[NG];
-#pragma unroll
-        for (int g = 0; g < NG; ++g) m[g] = group_mask(o, K, g);
+            // ---- reference window: masked words to shared memory
+            __syncwarp(hmask);                             // previous hypothesis' readers are done
+            for (int idx = lih; idx < K * NG; idx += LPH) {
+                const int rr = idx / NG, g = idx - rr * NG;
+                const uint32_t mg = group_mask(o, K, g);
+                uint32_t w = 0u;
+                if (mg) w = __ldg(reinterpret_cast<const uint32_t*>(base + rr * rowpitch + g * gstride + 4 * r)) & mg;
+                sref[rr][g] = w;
+            }
+            __syncwarp(hmask);
 
-        // ---- reference window: masked words to shared memory, its sums reduced over the lane group
-        int Sr = 0, SSr = 0;
-        __syncwarp(hmask);                                 // previous hypothesis' readers are done
-        for (int idx = lih; idx < K * NG; idx += LPH) {
-            const int rr = idx / NG, g = idx - rr * NG;
-            const uint32_t mg = group_mask(o, K, g);
-            uint32_t w = 0u;
-            if (mg) w = __ldg(reinterpret_cast<const uint32_t*>(base + rr * rowpitch + g * gstride + 4 * r)) & mg;
-            sref[rr][g] = w;
-            Sr = dp4a_u(w, 0x01010101u, Sr);
-            SSr = dp4a_u(w, w, SSr);
-        }
-        Sr = __reduce_add_sync(hmask, Sr);
-        SSr = __reduce_add_sync(hmask, SSr);
-        __syncwarp(hmask);
-        const long long var_r = (long long)NPIX * SSr - (long long)Sr * Sr;
-
-        double acc = 0.0;
-        int count = 0;
-        uint32_t myword = 0;
-        for (int p = 0; p < passes; ++p) {
-            const int qq = p * LPH + lih;                  // this lane's quad: views 4qq..4qq+3
-            const bool act = qq < Q;
-            int S[4] = {0, 0, 0, 0}, SS[4] = {0, 0, 0, 0}, SAB[4] = {0, 0, 0, 0};
-            const uint8_t* pq = base + (int64_t)qq * 16;
+            double acc = 0.0;
+            int count = 0;
+            uint32_t myword = 0;
+            for (int p = 0; p < passes; ++p) {
+                const int qq = p * LPH + lih;              // this lane's quad: views 4qq..4qq+3
+                const bool act = qq < Q;
+                const int qc = act ? qq : Q - 1;           // idle lanes shadow the last quad (same L1 lines)
+                const uint2 s2 = __ldg(reinterpret_cast<const uint2*>(smap + mi + 4 * qc));
+                const uint4 v4 = __ldg(reinterpret_cast<const uint4*>(vmap + mi + 4 * qc));
+                int SAB[4] = {0, 0, 0, 0};
+                const uint8_t* pq = base + (int64_t)qc * 16;
 #pragma unroll
-            for (int rr = 0; rr < K; ++rr) {
-                uint32_t rw[NG];
-                if constexpr (NG == 4) {
-                    const uint4 t4 = *reinterpret_cast<const uint4*>(&sref[rr][0]);
-                    rw[0] = t4.x; rw[1] = t4.y; rw[2] = t4.z; rw[3] = t4.w;
-                } else {
+                for (int rr = 0; rr < K; ++rr) {
+                    uint32_t rw[NG];
+                    if constexpr (NG == 4) {
+                        const uint4 t4 = *reinterpret_cast<const uint4*>(&sref[rr][0]);
+                        rw[0] = t4.x; rw[1] = t4.y; rw[2] = t4.z; rw[3] = t4.w;
+                    } else {
 #pragma unroll
-                    for (int g = 0; g < NG; ++g) rw[g] = sref[rr][g];
-                }
+                        for (int g = 0; g < NG; ++g) rw[g] = sref[rr][g];
+                    }
 #pragma unroll
-                for (int g = 0; g < NG; ++g) {
-                    if (m[g] != 0u && act) {
-                        const uint4 w4 = __ldg(reinterpret_cast<const uint4*>(pq + rr * rowpitch + g * gstride));
-                        const uint32_t w[4] = {w4.x & m[g], w4.y & m[g], w4.z & m[g], w4.w & m[g]};
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            S[k] = dp4a_u(w[k], 0x01010101u, S[k]);
-                            SS[k] = dp4a_u(w[k], w[k], SS[k]);
-                            SAB[k] = dp4a_u(w[k], rw[g], SAB[k]);
-                        }
+                    for (int g = 0; g < NG; ++g) {
+                        const uint4 w4 = __ldg(reinterpret_cast<const uint4*>(pq + rr * rowpitch + goff[g]));
+                        SAB[0] = dp4a_u(w4.x, rw[g], SAB[0]);
+                        SAB[1] = dp4a_u(w4.y, rw[g], SAB[1]);
+                        SAB[2] = dp4a_u(w4.z, rw[g], SAB[2]);
+                        SAB[3] = dp4a_u(w4.w, rw[g], SAB[3]);
                     }
                 }
-            }
-            // ---- this lane finishes its own four views
-            uint32_t nib = 0;
+                // ---- this lane finishes its own four views
+                const int Sv[4] = {(int)(s2.x & 0xffffu), (int)(s2.x >> 16), (int)(s2.y & 0xffffu), (int)(s2.y >> 16)};
+                const uint32_t var[4] = {v4.x, v4.y, v4.z, v4.w};
+                uint32_t nib = 0;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int v = 4 * qq + k;
-                bool defined;
-                const double val = ncc_from_sums(NPIX, S[k], SS[k], SAB[k], Sr, var_r, defined);
-                const bool scored = act && (v < V) && (v != r) && defined;
-                const bool vis = scored && (val > thr);
-                if (vis) {
-                    acc += val;
-                    nib |= 1u << k;
+                for (int k = 0; k < 4; ++k) {
+                    const int v = 4 * qq + k;
+                    // exact integers: n*SAB, S*Sr <= 225^2 * 255^2 need 64 bits at wid > 5
+                    const double num = (WID <= 5) ? (double)(NPIX * SAB[k] - Sv[k] * Sr)
+                                                  : (double)((long long)NPIX * SAB[k] - (long long)Sv[k] * Sr);
+                    const bool defined = (var[k] != 0u) && (var_r != 0.0);
+                    const double val = ncc_ratio(num, (double)var[k], var_r, cn, thr);
+                    const bool scored = act && (v < V) && (v != r) && defined;
+                    const bool vis = scored && (val > thr);
+                    if (vis) {
+                        acc += val;
+                        nib |= 1u << k;
+                    }
+                    if (ncc_out && act && v < V) ncc_out[h * V + v] = scored ? (float)val : nanf("");
                 }
-                if (ncc_out && act && v < V) ncc_out[h * V + v] = scored ? (float)val : nanf("");
-            }
-            // lane group covers LPH*4 mask bits per pass = max(LPH/8, 1) 32-bit words
-            constexpr int WPP = LPH >= 8 ? LPH / 8 : 1;
+                // the lane group covers LPH*4 mask bits per pass = max(LPH/8, 1) 32-bit words
+                constexpr int WPP = LPH >= 8 ? LPH / 8 : 1;
 #pragma unroll
-            for (int w = 0; w < WPP; ++w) {
-                const uint32_t contrib = ((lih >> 3) == w) ? (nib << (4 * (lih & 7))) : 0u;
-                const uint32_t word = __reduce_or_sync(hmask, contrib);
-                count += __popc(word);
-                if (lih == p * WPP + w) myword = word;     // word index < 32 <=> V <= 1024
+                for (int w = 0; w < WPP; ++w) {
+                    const uint32_t contrib = ((lih >> 3) == w) ? (nib << (4 * (lih & 7))) : 0u;
+                    const uint32_t word = __reduce_or_sync(hmask, contrib);
+                    count += __popc(word);
+                    if (lih == p * WPP + w) myword = word; // word index < 32 <=> V <= 1024
+                }
             }
-        }
 #pragma unroll
-        for (int s = LPH / 2; s > 0; s >>= 1) acc += __shfl_xor_sync(hmask, acc, s);
-        for (int w = lih; w < mask_words32; w += LPH)
-            reinterpret_cast<uint32_t*>(vis_out)[h * mask_words32 + w] = (w == lih) ? myword : 0u;
-        if (lih == 0) {
-            count_out[h] = count;
-            if (avg_out) avg_out[h] = count > 0 ? acc / (double)count : 0.0;
+            for (int s = LPH / 2; s > 0; s >>= 1) acc += __shfl_xor_sync(hmask, acc, s);
+            for (int w = lih; w < mask_words32; w += LPH)
+                reinterpret_cast<uint32_t*>(vis_out)[h * mask_words32 + w] = (w == lih) ? myword : 0u;
+            if (lih == 0) {
+                count_out[h] = count;
+                if (avg_out) avg_out[h] = count > 0 ? acc / (double)count : 0.0;
+            }
         }
     }
 }
 
+template <int WID, int LPH>
+static int launch_gather_lph(mvs_ctx* ctx, int64_t N, const uint32_t* anchors, const int32_t* order, const int32_t* ref,
+                             double thr, uint64_t* vis, double* avg, int32_t* count, float* ncc, cudaStream_t s) {
+    auto kern = ncc_score_gather<WID, LPH>;
+    static bool configured = false;                        // per instantiation: prefer L1 over shared memory
+    if (!configured) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+        configured = true;
+    }
+    const int64_t chunk = 8 * (32 / LPH) * 8;
+    const int64_t want = (N + chunk - 1) / chunk;
+    const int64_t cap = (int64_t)ctx->sm_count * 2 * 8;
+    const int blocks = (int)(want < cap ? want : cap);
+    kern<<<blocks, 256, 0, s>>>(ctx->d_gray, ctx->d_smap, ctx->d_vmap, ctx->V, ctx->Vp, ctx->Q, ctx->W, ctx->gstride,
+                                ctx->rowpitch, N, anchors, order, ref, thr, vis, avg, count, ncc);
+    return MVS_OK;
+}
+
 template <int WID>
-static void launch_gather(mvs_ctx* ctx, int blocks_cap, int64_t N, const double* c, const int32_t* ref, double thr,
-                          uint64_t* vis, double* avg, int32_t* count, double* xy, float* ncc, cudaStream_t s) {
+static int launch_gather(mvs_ctx* ctx, int64_t N, const uint32_t* anchors, const int32_t* order, const int32_t* ref,
+                         double thr, uint64_t* vis, double* avg, int32_t* count, float* ncc, cudaStream_t s) {
     const int Q = ctx->Q;
-#define MVS_LAUNCH(LPH)                                                                                              \
-    do {                                                                                                             \
-        const int64_t per_block = 8 * (32 / LPH);                                                                    \
-        int64_t want = (N + per_block - 1) / per_block;                                                              \
-        const int blocks = (int)(want < blocks_cap ? want : blocks_cap);                                             \
-        ncc_score_gather<WID, LPH><<<blocks, 256, 0, s>>>(ctx->d_gray, ctx->d_cam, ctx->V, Q, ctx->H, ctx->W,         \
-                                                          ctx->gstride, ctx->rowpitch, N, c, ref, thr, vis, avg,     \
-                                                          count, xy, ncc);                                           \
-    } while (0)
-    if (Q <= 4)
-        MVS_LAUNCH(4);
-    else if (Q <= 8)
-        MVS_LAUNCH(8);
-    else if (Q <= 16)
-        MVS_LAUNCH(16);
-    else
-        MVS_LAUNCH(32);
-#undef MVS_LAUNCH
+    if (Q <= 4) return launch_gather_lph<WID, 4>(ctx, N, anchors, order, ref, thr, vis, avg, count, ncc, s);
+    if (Q <= 8) return launch_gather_lph<WID, 8>(ctx, N, anchors, order, ref, thr, vis, avg, count, ncc, s);
+    if (Q <= 16) return launch_gather_lph<WID, 16>(ctx, N, anchors, order, ref, thr, vis, avg, count, ncc, s);
+    return launch_gather_lph<WID, 32>(ctx, N, anchors, order, ref, thr, vis, avg, count, ncc, s);
 }
 
 int mvs_launch_score_refexact(mvs_ctx* ctx, int64_t N, const double* c, const int32_t* ref, double thr, int wid,
                               uint64_t* vis, double* avg, int32_t* count, double* xy, float* ncc, cudaStream_t s) {
     if (N == 0) return MVS_OK;
-    const int cap = ctx->sm_count * 2 * 4;                 // 2 resident CTAs/SM, x4 for tail balance
+    if (wid < 1 || wid > 7) {
+        mvs_set_error("wid %d not supported (1..7)", wid);
+        return MVS_ERR_ARG;
+    }
+    int rc;
+    if ((rc = mvs_build_window_maps(ctx, wid, s)) != MVS_OK) return rc;
+    const bool sort = N >= MVS_SORT_MIN;
+    if ((rc = mvs_bin_hypotheses(ctx, N, c, ref, wid, sort, vis, avg, count, xy, ncc, s)) != MVS_OK) return rc;
+    const uint32_t* anchors = sort ? ctx->d_bin_sanchor : ctx->d_bin_anchor;
+    const int32_t* order = sort ? ctx->d_bin_order : nullptr;
+    const int pslot = (int)(ctx->prof_n % MVS_PROF_RING);
+    if (ctx->profile) MVS_CUDA_CHECK(cudaEventRecord(ctx->prof_ev[2 * pslot], s));
     switch (wid) {
-        case 1: launch_gather<1>(ctx, cap, N, c, ref, thr, vis, avg, count, xy, ncc, s); break;
-        case 2: launch_gather<2>(ctx, cap, N, c, ref, thr, vis, avg, count, xy, ncc, s); break;
-        case 3: launch_gather<3>(ctx, cap, N, c, ref, thr, vis, avg, count, xy, ncc, s); break;
-        case 4: launch_gather<4>(ctx, cap, N, c, ref, thr, vis, avg, count, xy, ncc, s); break;
-        case 5: launch_gather<5>(ctx, cap, N, c, ref, thr, vis, avg, count, xy, ncc, s); break;
-        case 6: launch_gather<6>(ctx, cap, N, c, ref, thr, vis, avg, count, xy, ncc, s); break;
-        case 7: launch_gather<7>(ctx, cap, N, c, ref, thr, vis, avg, count, xy, ncc, s); break;
-        default: mvs_set_error("wid %d not supported (1..7)", wid); return MVS_ERR_ARG;
+        case 1: rc = launch_gather<1>(ctx, N, anchors, order, ref, thr, vis, avg, count, ncc, s); break;
+        case 2: rc = launch_gather<2>(ctx, N, anchors, order, ref, thr, vis, avg, count, ncc, s); break;
+        case 3: rc = launch_gather<3>(ctx, N, anchors, order, ref, thr, vis, avg, count, ncc, s); break;
+        case 4: rc = launch_gather<4>(ctx, N, anchors, order, ref, thr, vis, avg, count, ncc, s); break;
+        case 5: rc = launch_gather<5>(ctx, N, anchors, order, ref, thr, vis, avg, count, ncc, s); break;
+        case 6: rc = launch_gather<6>(ctx, N, anchors, order, ref, thr, vis, avg, count, ncc, s); break;
+        default: rc = launch_gather<7>(ctx, N, anchors, order, ref, thr, vis, avg, count, ncc, s); break;
+    }
+    if (ctx->profile) {
+        MVS_CUDA_CHECK(cudaEventRecord(ctx->prof_ev[2 * pslot + 1], s));
+        ctx->prof_n++;
     }
     ctx->launches++;
     MVS_CUDA_CHECK(cudaGetLastError());
-    return MVS_OK;
+    return rc;
 }
