@@ -3,8 +3,10 @@
 // Mode A samples every view at the reference view's projection (MVS2.py:63,68), so two
 // hypotheses whose anchors are a few pixels apart read almost the same bytes of the
 // view-interleaved stack, whatever their reference views are.  Ordering a batch by
-// 8x8-pixel anchor tile turns the per-hypothesis gather (V*121 bytes each) into L1 hits:
-// a tile's bytes are fetched from L2 about once per CTA instead of once per hypothesis.
+// (8x8-pixel anchor tile, row, first pixel group of the window) turns the per-hypothesis
+// gather (V*121 bytes each) into L1 hits -- a tile's bytes are fetched from L2 about once
+// per CTA instead of once per hypothesis -- and puts hypotheses that read exactly the
+// same 16-byte quads next to each other, so K1 loads them once for two hypotheses.
 //   bin_project : one thread per hypothesis -- fp64 projection in cv2's operation order
 //                 (utils.py:241-244), int() truncation and the bounds rule of
 //                 HarrisFeatures.py:128; writes xy, the packed anchor, the empty result of
@@ -45,7 +47,9 @@ __global__ void __launch_bounds__(256)
                 for (int v = 0; v < V; ++v) ncc_out[h * V + v] = nanf("");
         }
         if (hist) {
-            const int k = valid ? (row >> MVS_BIN_SHIFT) * tiles_x + (col >> MVS_BIN_SHIFT) : n_tiles;
+            // bins = (row, first pixel group of the window), ordered tile by tile (8 rows x 2 groups)
+            const int cg = (col - wid) >> 2;
+            const int k = valid ? (((row >> 3) * tiles_x + (cg >> 1)) << 4) + ((row & 7) << 1) + (cg & 1) : n_tiles;
             key[h] = k;
             rank[h] = atomicAdd(hist + k, 1);
         }
@@ -72,8 +76,8 @@ int mvs_bin_hypotheses(mvs_ctx* ctx, int64_t N, const double* c, const int32_t* 
     }
     if ((rc = mvs_ensure((void**)&ctx->d_bin_anchor, &ctx->bin_anchor_bytes, sizeof(uint32_t) * N, "anchors")) != MVS_OK)
         return rc;
-    const int tiles_x = (ctx->W >> MVS_BIN_SHIFT) + 1, tiles_y = (ctx->H >> MVS_BIN_SHIFT) + 1;
-    const int n_tiles = tiles_x * tiles_y;
+    const int tiles_x = (ctx->W >> 3) + 1, tiles_y = (ctx->H >> 3) + 1;
+    const int n_tiles = tiles_x * tiles_y * 16;            // bins: 16 (row, pixel group) cells per tile
     if (sort) {
         if ((rc = mvs_ensure((void**)&ctx->d_bin_hist, &ctx->bin_hist_bytes, sizeof(int32_t) * (n_tiles + 2), "tile histogram")) != MVS_OK ||
             (rc = mvs_ensure((void**)&ctx->d_bin_key, &ctx->bin_key_bytes, sizeof(int32_t) * N, "tile keys")) != MVS_OK ||

@@ -24,6 +24,7 @@
 // contraction.
 #include "project.cuh"
 #include "scan.cuh"
+#include <stdlib.h>
 
 #define FULL 0xffffffffu
 
@@ -192,180 +193,310 @@ __device__ __forceinline__ uint32_t hyp_mask(int sub) {
     }
 }
 
-// ncc = (num / sqrt(var_i * var_r)) * n/(n-1), oracle/mode_a.py::score operation order.
-// Fast path: num * rsqrt(den) * n/(n-1) is within a few ulp of that; only a value closer
-// than 1e-9 to the threshold is recomputed with the correctly rounded sqrt and division,
-// so the strict '>' decision is always the oracle's.
-__device__ __forceinline__ double ncc_ratio(double num, double var_i, double var_r, double cn, double thr) {
-    const double den = var_i * var_r;
-    double val = (num * rsqrt(den)) * cn;
-    if (__builtin_expect(fabs(val - thr) < 1e-9, 0)) val = (num / sqrt(den)) * cn;
-    return val;
+// ncc = (num / sqrt(var_i * var_r)) * n/(n-1), oracle/mode_a.py::score operation order,
+// with the correctly rounded fp64 sqrt and division.  Out of line: it only runs for values
+// closer than 1e-9 to the threshold.
+__device__ __noinline__ double ncc_exact(double num, double var_i, double var_r, double cn) {
+    return (num / sqrt(var_i * var_r)) * cn;
 }
 
-// ---------------------------------------------------------------------------------
-// K1: LPH lanes per hypothesis, 32/LPH hypotheses per warp.  A CTA walks chunks of
-// CHUNK consecutive positions of the (tile-ordered) batch so that its lane groups share
-// L1 lines.  anchors[i] = row<<16|col of position i (MVS_ANCHOR_INVALID: rejected,
-// result already written by bin_project); order[i] = hypothesis index (NULL: identity).
-// ---------------------------------------------------------------------------------
-template <int WID, int LPH>
-__global__ void __launch_bounds__(256, 2)
-    ncc_score_gather(const uint8_t* __restrict__ gray4, const uint16_t* __restrict__ smap, const uint32_t* __restrict__ vmap,
-                     int V, int Vp, int Q, int W, int64_t gstride, int64_t rowpitch, int64_t N,
-                     const uint32_t* __restrict__ anchors, const int32_t* __restrict__ order,
-                     const int32_t* __restrict__ ref, double thr, uint64_t* __restrict__ vis_out,
-                     double* __restrict__ avg_out, int32_t* __restrict__ count_out, float* __restrict__ ncc_out) {
+// u32 / s32 -> fp64 on the fp64 pipe (magic-number add) instead of the conversion unit
+__device__ __forceinline__ double u32_to_double(uint32_t u) {
+    return __hiloint2double(0x43300000, (int)u) - 4503599627370496.0;                 // 2^52 + u - 2^52
+}
+__device__ __forceinline__ double s32_to_double(int i) {
+    return __hiloint2double(0x43300000, i ^ 0x80000000) - 4503601774854144.0;         // 2^52 + 2^31
+}
+
+// Fast path of the ratio: y0 = rsqrt.approx(den) (MUFU.RSQ64H, ~2^-22) plus one Newton
+// step gives rsqrt(den) to ~1e-13 relative.  var_r_scaled = var_r * ((n-1)/n)^2 folds the
+// n/(n-1) factor in, so val = num * rsqrt(var_i * var_r_scaled).  The caller re-does any
+// value within 1e-9 of the threshold with ncc_exact, so the strict '>' decision is always
+// the oracle's; the value itself differs from the oracle's by < 1e-12.
+__device__ __forceinline__ double ncc_fast(double num, double var_i, double var_r_scaled) {
+    const double den = var_i * var_r_scaled;
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(den));
+    const double t = y * y;
+    const double e = fma(-0.5 * den, t, 1.5);
+    return num * (y * e);
+}
+
+struct ScoreArgs {
+    const uint8_t* gray4;
+    const uint16_t* smap;
+    const uint32_t* vmap;
+    int V, Vp, Q, W;
+    int64_t gstride, rowpitch;
+    const int32_t* ref;
+    double thr;
+    uint64_t* vis_out;
+    double* avg_out;
+    int32_t* count_out;
+    float* ncc_out;
+};
+
+// Score NB hypotheses (NB = 1 or 2) that share the window row AND the first pixel group,
+// i.e. the same (row, (col - WID) >> 2): they read exactly the same 16-byte quads of every
+// view, so each quad is loaded ONCE and multiplied against NB reference windows.  GS is the
+// compile-time byte stride between pixel groups (4*Vp) or 0 = read it from the arguments.
+template <int WID, int LPH, int NB, int GS>
+__device__ __forceinline__ void score_block(const ScoreArgs& A, const uint32_t (&anchor)[NB], const int64_t (&h)[NB],
+                                            uint32_t (*sref)[2 * WID + 1][(2 * WID + 7) / 4], int lih, uint32_t hmask) {
     constexpr int K = 2 * WID + 1;
     constexpr int NG = (K + 6) / 4;            // pixel groups a K-pixel run at offset 0..3 can touch
     constexpr int NPIX = K * K;
+    const int64_t gstride = GS ? (int64_t)GS : A.gstride;
+    const int mask_words32 = 2 * ((A.V + 63) >> 6);        // 32-bit chunks per hypothesis in vis_out
+    const int passes = (LPH == 32) ? (A.Q + 31) >> 5 : 1;
+    const double cn = (double)NPIX / (double)(NPIX - 1);
+
+    const int row = (int)(anchor[0] >> 16);
+    const int cg = ((int)(anchor[0] & 0xffffu) - WID) >> 2;
+    const uint8_t* base = A.gray4 + (int64_t)(row - WID) * A.rowpitch + (int64_t)cg * gstride;
+    int r[NB], o[NB], Sr[NB];
+    int64_t mi[NB];
+    double var_r[NB], var_rs[NB];
+    bool need_last = false;                                // only the last pixel group can be empty
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        const int col = (int)(anchor[b] & 0xffffu);
+        r[b] = __ldg(A.ref + h[b]);
+        o[b] = (col - WID) & 3;
+        mi[b] = ((int64_t)row * A.W + col) * A.Vp;
+        Sr[b] = (int)__ldg(A.smap + mi[b] + r[b]);
+        var_r[b] = (double)__ldg(A.vmap + mi[b] + r[b]);
+        var_rs[b] = var_r[b] * ((double)((NPIX - 1) * (NPIX - 1)) / (double)(NPIX * NPIX));
+        need_last |= group_mask(o[b], K, NG - 1) != 0u;
+    }
+    // an unused last group re-reads group 0 (an L1 hit) against zero reference words
+    const uint32_t lastoff = need_last ? (uint32_t)((NG - 1) * gstride) : 0u;
+
+    // ---- reference windows: masked words to shared memory
+    __syncwarp(hmask);                                     // the previous block's readers are done
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        if constexpr (LPH % NG == 0) {                     // a lane always stages the same pixel group
+            const int g = lih % NG;
+            const uint32_t mg = group_mask(o[b], K, g);
+            const uint8_t* pr = base + g * gstride + 4 * r[b] + (lih / NG) * A.rowpitch;
+            for (int rr = lih / NG; rr < K; rr += LPH / NG) {
+                sref[b][rr][g] = mg ? (__ldg(reinterpret_cast<const uint32_t*>(pr)) & mg) : 0u;
+                pr += (LPH / NG) * A.rowpitch;
+            }
+        } else {
+            for (int idx = lih; idx < K * NG; idx += LPH) {
+                const int rr = idx / NG, g = idx - rr * NG;
+                const uint32_t mg = group_mask(o[b], K, g);
+                uint32_t w = 0u;
+                if (mg) w = __ldg(reinterpret_cast<const uint32_t*>(base + rr * A.rowpitch + g * gstride + 4 * r[b])) & mg;
+                sref[b][rr][g] = w;
+            }
+        }
+    }
+    __syncwarp(hmask);
+
+    double acc[NB];
+    int count[NB];
+    uint32_t myword[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        acc[b] = 0.0;
+        count[b] = 0;
+        myword[b] = 0u;
+    }
+    for (int p = 0; p < passes; ++p) {
+        const int qq = p * LPH + lih;                      // this lane's quad: views 4qq..4qq+3
+        const bool act = qq < A.Q;
+        const int qc = act ? qq : A.Q - 1;                 // idle lanes shadow the last quad (same L1 lines)
+        uint2 s2[NB];
+        uint4 v4[NB];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            s2[b] = __ldg(reinterpret_cast<const uint2*>(A.smap + mi[b] + 4 * qc));
+            v4[b] = __ldg(reinterpret_cast<const uint4*>(A.vmap + mi[b] + 4 * qc));
+        }
+        int SAB[NB][4];
+#pragma unroll
+        for (int b = 0; b < NB; ++b)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) SAB[b][k] = 0;
+        const uint8_t* prow = base + (int64_t)qc * 16;
+#pragma unroll
+        for (int rr = 0; rr < K; ++rr) {
+            uint32_t rw[NB][NG];
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                if constexpr (NG == 4) {
+                    const uint4 t4 = *reinterpret_cast<const uint4*>(&sref[b][rr][0]);
+                    rw[b][0] = t4.x; rw[b][1] = t4.y; rw[b][2] = t4.z; rw[b][3] = t4.w;
+                } else {
+#pragma unroll
+                    for (int g = 0; g < NG; ++g) rw[b][g] = sref[b][rr][g];
+                }
+            }
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                const uint8_t* pw = (g == NG - 1) ? prow + lastoff : prow + g * gstride;
+                const uint4 w4 = __ldg(reinterpret_cast<const uint4*>(pw));
+#pragma unroll
+                for (int b = 0; b < NB; ++b) {
+                    SAB[b][0] = dp4a_u(w4.x, rw[b][g], SAB[b][0]);
+                    SAB[b][1] = dp4a_u(w4.y, rw[b][g], SAB[b][1]);
+                    SAB[b][2] = dp4a_u(w4.z, rw[b][g], SAB[b][2]);
+                    SAB[b][3] = dp4a_u(w4.w, rw[b][g], SAB[b][3]);
+                }
+            }
+            prow += A.rowpitch;
+        }
+        // ---- this lane finishes its own four views of every hypothesis of the block
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const int Sv[4] = {(int)(s2[b].x & 0xffffu), (int)(s2[b].x >> 16), (int)(s2[b].y & 0xffffu), (int)(s2[b].y >> 16)};
+            const uint32_t var[4] = {v4[b].x, v4[b].y, v4[b].z, v4[b].w};
+            float* nrow = (A.ncc_out && act) ? A.ncc_out + h[b] * A.V + 4 * qq : nullptr;
+            uint32_t nib = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int v = 4 * qq + k;
+                // exact integers: n*SAB, S*Sr <= 225^2 * 255^2 need 64 bits at wid > 5
+                const double num = (WID <= 5) ? s32_to_double(NPIX * SAB[b][k] - Sv[k] * Sr[b])
+                                              : (double)((long long)NPIX * SAB[b][k] - (long long)Sv[k] * Sr[b]);
+                const double var_i = u32_to_double(var[k]);
+                double val = ncc_fast(num, var_i, var_rs[b]);
+                const bool scored = act && (v < A.V) && (v != r[b]) && (var[k] != 0u) && (var_r[b] != 0.0);
+                if (__builtin_expect(scored && fabs(val - A.thr) < 1e-9, 0)) val = ncc_exact(num, var_i, var_r[b], cn);
+                const bool vis = scored && (val > A.thr);
+                acc[b] += vis ? val : 0.0;
+                nib |= vis ? (1u << k) : 0u;
+                if (nrow && v < A.V) nrow[k] = scored ? (float)val : nanf("");
+            }
+            // the lane group covers LPH*4 mask bits per pass = max(LPH/8, 1) 32-bit words
+            constexpr int WPP = LPH >= 8 ? LPH / 8 : 1;
+#pragma unroll
+            for (int w = 0; w < WPP; ++w) {
+                const uint32_t contrib = ((lih >> 3) == w) ? (nib << (4 * (lih & 7))) : 0u;
+                const uint32_t word = __reduce_or_sync(hmask, contrib);
+                count[b] += __popc(word);
+                if (lih == p * WPP + w) myword[b] = word;  // word index < 32 <=> V <= 1024
+            }
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        double a = acc[b];
+#pragma unroll
+        for (int s = LPH / 2; s > 0; s >>= 1) a += __shfl_xor_sync(hmask, a, s);
+        for (int w = lih; w < mask_words32; w += LPH)
+            reinterpret_cast<uint32_t*>(A.vis_out)[h[b] * mask_words32 + w] = (w == lih) ? myword[b] : 0u;
+        if (lih == 0) {
+            A.count_out[h[b]] = count[b];
+            if (A.avg_out) A.avg_out[h[b]] = count[b] > 0 ? a / (double)count[b] : 0.0;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// K1: LPH lanes per hypothesis PAIR, 32/LPH pairs per warp.  A CTA walks chunks of
+// consecutive positions of the (row, pixel-group)-ordered batch so that its lane groups
+// share L1 lines; two neighbouring positions with the same (row, pixel group) are scored
+// as one block with shared loads.  anchors[i] = row<<16|col of position i
+// (MVS_ANCHOR_INVALID: rejected, result already written by bin_project); order[i] =
+// hypothesis index (NULL: identity).
+// ---------------------------------------------------------------------------------
+template <int WID, int LPH, int GS, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+    ncc_score_gather(const ScoreArgs A, int64_t N, const uint32_t* __restrict__ anchors, const int32_t* __restrict__ order) {
+    constexpr int K = 2 * WID + 1;
+    constexpr int NG = (K + 6) / 4;
     constexpr int HPW = 32 / LPH;
-    constexpr int ITERS = 8;
-    constexpr int CHUNK = 8 * HPW * ITERS;
-    __shared__ __align__(16) uint32_t s_ref[8][HPW][K][NG];
+    constexpr int ITERS = 4;
+    constexpr int CHUNK = 8 * HPW * 2 * ITERS;
+    __shared__ __align__(16) uint32_t s_ref[8][HPW][2][K][NG];
 
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     const int sub = lane / LPH;
     const int lih = lane % LPH;
     const uint32_t hmask = hyp_mask<LPH>(sub);
-    const int mask_words32 = 2 * ((V + 63) >> 6);          // 32-bit chunks per hypothesis in vis_out
-    const int passes = (LPH == 32) ? (Q + 31) >> 5 : 1;
-    const double cn = (double)NPIX / (double)(NPIX - 1);
-    uint32_t(*sref)[NG] = s_ref[wib][sub];
+    uint32_t(*sref)[K][NG] = s_ref[wib][sub];
 
     for (int64_t i0 = (int64_t)blockIdx.x * CHUNK; i0 < N; i0 += (int64_t)gridDim.x * CHUNK) {
         for (int it = 0; it < ITERS; ++it) {
-            const int64_t i = i0 + (it * 8 + wib) * HPW + sub;
+            const int64_t i = i0 + 2 * ((it * 8 + wib) * HPW + sub);
             if (i >= N) continue;                          // the whole lane group leaves together
-            const uint32_t a = __ldg(anchors + i);
-            if (a == MVS_ANCHOR_INVALID) continue;
-            const int64_t h = order ? (int64_t)__ldg(order + i) : i;
-            const int r = __ldg(ref + h);
-            const int row = (int)(a >> 16), col = (int)(a & 0xffffu);
-            const int o = (col - WID) & 3;                 // offset of the window inside its first pixel group
-            const uint8_t* base = gray4 + (int64_t)(row - WID) * rowpitch + (int64_t)((col - WID) >> 2) * gstride;
-            const int64_t mi = ((int64_t)row * W + col) * Vp;
-            const int Sr = (int)__ldg(smap + mi + r);
-            const double var_r = (double)__ldg(vmap + mi + r);
-            // byte masks of the window inside each pixel group; empty groups re-read group 0
-            // (an L1 hit) against a zero reference word instead of branching
-            uint32_t m[NG];
-            int64_t goff[NG];
-#pragma unroll
-            for (int g = 0; g < NG; ++g) {
-                m[g] = group_mask(o, K, g);
-                goff[g] = m[g] ? g * gstride : 0;
-            }
-            // ---- reference window: masked words to shared memory
-            __syncwarp(hmask);                             // previous hypothesis' readers are done
-            for (int idx = lih; idx < K * NG; idx += LPH) {
-                const int rr = idx / NG, g = idx - rr * NG;
-                const uint32_t mg = group_mask(o, K, g);
-                uint32_t w = 0u;
-                if (mg) w = __ldg(reinterpret_cast<const uint32_t*>(base + rr * rowpitch + g * gstride + 4 * r)) & mg;
-                sref[rr][g] = w;
-            }
-            __syncwarp(hmask);
-
-            double acc = 0.0;
-            int count = 0;
-            uint32_t myword = 0;
-            for (int p = 0; p < passes; ++p) {
-                const int qq = p * LPH + lih;              // this lane's quad: views 4qq..4qq+3
-                const bool act = qq < Q;
-                const int qc = act ? qq : Q - 1;           // idle lanes shadow the last quad (same L1 lines)
-                const uint2 s2 = __ldg(reinterpret_cast<const uint2*>(smap + mi + 4 * qc));
-                const uint4 v4 = __ldg(reinterpret_cast<const uint4*>(vmap + mi + 4 * qc));
-                int SAB[4] = {0, 0, 0, 0};
-                const uint8_t* pq = base + (int64_t)qc * 16;
-#pragma unroll
-                for (int rr = 0; rr < K; ++rr) {
-                    uint32_t rw[NG];
-                    if constexpr (NG == 4) {
-                        const uint4 t4 = *reinterpret_cast<const uint4*>(&sref[rr][0]);
-                        rw[0] = t4.x; rw[1] = t4.y; rw[2] = t4.z; rw[3] = t4.w;
-                    } else {
-#pragma unroll
-                        for (int g = 0; g < NG; ++g) rw[g] = sref[rr][g];
-                    }
-#pragma unroll
-                    for (int g = 0; g < NG; ++g) {
-                        const uint4 w4 = __ldg(reinterpret_cast<const uint4*>(pq + rr * rowpitch + goff[g]));
-                        SAB[0] = dp4a_u(w4.x, rw[g], SAB[0]);
-                        SAB[1] = dp4a_u(w4.y, rw[g], SAB[1]);
-                        SAB[2] = dp4a_u(w4.z, rw[g], SAB[2]);
-                        SAB[3] = dp4a_u(w4.w, rw[g], SAB[3]);
-                    }
+            const uint32_t a0 = __ldg(anchors + i);
+            const uint32_t a1 = (i + 1 < N) ? __ldg(anchors + i + 1) : MVS_ANCHOR_INVALID;
+            const bool ok0 = a0 != MVS_ANCHOR_INVALID, ok1 = a1 != MVS_ANCHOR_INVALID;
+            const int64_t h0 = order ? (int64_t)__ldg(order + i) : i;
+            const int64_t h1 = (order && ok1) ? (int64_t)__ldg(order + i + 1) : i + 1;
+            const bool same = ok0 && ok1 && ((a0 >> 16) == (a1 >> 16)) &&
+                              ((((int)(a0 & 0xffffu) - WID) >> 2) == (((int)(a1 & 0xffffu) - WID) >> 2));
+            if (same) {
+                const uint32_t aa[2] = {a0, a1};
+                const int64_t hh[2] = {h0, h1};
+                score_block<WID, LPH, 2, GS>(A, aa, hh, sref, lih, hmask);
+            } else {
+                const uint32_t a2[2] = {a0, a1};
+                const int64_t h2[2] = {h0, h1};
+#pragma unroll 1
+                for (int t = 0; t < 2; ++t) {              // one code instance for both singles
+                    if (a2[t] == MVS_ANCHOR_INVALID) continue;
+                    const uint32_t aa[1] = {a2[t]};
+                    const int64_t hh[1] = {h2[t]};
+                    score_block<WID, LPH, 1, GS>(A, aa, hh, sref, lih, hmask);
                 }
-                // ---- this lane finishes its own four views
-                const int Sv[4] = {(int)(s2.x & 0xffffu), (int)(s2.x >> 16), (int)(s2.y & 0xffffu), (int)(s2.y >> 16)};
-                const uint32_t var[4] = {v4.x, v4.y, v4.z, v4.w};
-                uint32_t nib = 0;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int v = 4 * qq + k;
-                    // exact integers: n*SAB, S*Sr <= 225^2 * 255^2 need 64 bits at wid > 5
-                    const double num = (WID <= 5) ? (double)(NPIX * SAB[k] - Sv[k] * Sr)
-                                                  : (double)((long long)NPIX * SAB[k] - (long long)Sv[k] * Sr);
-                    const bool defined = (var[k] != 0u) && (var_r != 0.0);
-                    const double val = ncc_ratio(num, (double)var[k], var_r, cn, thr);
-                    const bool scored = act && (v < V) && (v != r) && defined;
-                    const bool vis = scored && (val > thr);
-                    if (vis) {
-                        acc += val;
-                        nib |= 1u << k;
-                    }
-                    if (ncc_out && act && v < V) ncc_out[h * V + v] = scored ? (float)val : nanf("");
-                }
-                // the lane group covers LPH*4 mask bits per pass = max(LPH/8, 1) 32-bit words
-                constexpr int WPP = LPH >= 8 ? LPH / 8 : 1;
-#pragma unroll
-                for (int w = 0; w < WPP; ++w) {
-                    const uint32_t contrib = ((lih >> 3) == w) ? (nib << (4 * (lih & 7))) : 0u;
-                    const uint32_t word = __reduce_or_sync(hmask, contrib);
-                    count += __popc(word);
-                    if (lih == p * WPP + w) myword = word; // word index < 32 <=> V <= 1024
-                }
-            }
-#pragma unroll
-            for (int s = LPH / 2; s > 0; s >>= 1) acc += __shfl_xor_sync(hmask, acc, s);
-            for (int w = lih; w < mask_words32; w += LPH)
-                reinterpret_cast<uint32_t*>(vis_out)[h * mask_words32 + w] = (w == lih) ? myword : 0u;
-            if (lih == 0) {
-                count_out[h] = count;
-                if (avg_out) avg_out[h] = count > 0 ? acc / (double)count : 0.0;
             }
         }
     }
 }
 
-template <int WID, int LPH>
-static int launch_gather_lph(mvs_ctx* ctx, int64_t N, const uint32_t* anchors, const int32_t* order, const int32_t* ref,
-                             double thr, uint64_t* vis, double* avg, int32_t* count, float* ncc, cudaStream_t s) {
-    auto kern = ncc_score_gather<WID, LPH>;
-    static bool configured = false;                        // per instantiation: prefer L1 over shared memory
-    if (!configured) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
-        configured = true;
-    }
-    const int64_t chunk = 8 * (32 / LPH) * 8;
+#ifndef MVS_K1_MINB
+#define MVS_K1_MINB 4
+#endif
+
+template <int WID, int LPH, int GS, int MINB = MVS_K1_MINB>
+static int launch_gather_gs(mvs_ctx* ctx, const ScoreArgs& A, int64_t N, const uint32_t* anchors, const int32_t* order,
+                            cudaStream_t s) {
+    auto kern = ncc_score_gather<WID, LPH, GS, MINB>;
+    const int64_t chunk = 8 * (32 / LPH) * 2 * 4;
     const int64_t want = (N + chunk - 1) / chunk;
-    const int64_t cap = (int64_t)ctx->sm_count * 2 * 8;
+    const int64_t cap = (int64_t)ctx->sm_count * MINB * 8;
     const int blocks = (int)(want < cap ? want : cap);
-    kern<<<blocks, 256, 0, s>>>(ctx->d_gray, ctx->d_smap, ctx->d_vmap, ctx->V, ctx->Vp, ctx->Q, ctx->W, ctx->gstride,
-                                ctx->rowpitch, N, anchors, order, ref, thr, vis, avg, count, ncc);
+    kern<<<blocks, 256, 0, s>>>(A, N, anchors, order);
     return MVS_OK;
 }
 
+// tuning knob for experiments on the headline configuration (resident CTAs per SM)
+static int k1_minb_override() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("MVS_K1_MINB");
+        v = e ? atoi(e) : 0;
+    }
+    return v;
+}
+
 template <int WID>
-static int launch_gather(mvs_ctx* ctx, int64_t N, const uint32_t* anchors, const int32_t* order, const int32_t* ref,
-                         double thr, uint64_t* vis, double* avg, int32_t* count, float* ncc, cudaStream_t s) {
+static int launch_gather(mvs_ctx* ctx, const ScoreArgs& A, int64_t N, const uint32_t* anchors, const int32_t* order,
+                         cudaStream_t s) {
     const int Q = ctx->Q;
-    if (Q <= 4) return launch_gather_lph<WID, 4>(ctx, N, anchors, order, ref, thr, vis, avg, count, ncc, s);
-    if (Q <= 8) return launch_gather_lph<WID, 8>(ctx, N, anchors, order, ref, thr, vis, avg, count, ncc, s);
-    if (Q <= 16) return launch_gather_lph<WID, 16>(ctx, N, anchors, order, ref, thr, vis, avg, count, ncc, s);
-    return launch_gather_lph<WID, 32>(ctx, N, anchors, order, ref, thr, vis, avg, count, ncc, s);
+    if (Q <= 4) return launch_gather_gs<WID, 4, 0>(ctx, A, N, anchors, order, s);
+    if (Q <= 8) return launch_gather_gs<WID, 8, 0>(ctx, A, N, anchors, order, s);
+    if (Q <= 16) {
+        // the reference's own configuration (wid 5, dinoRing's 48 views): group stride as an immediate
+        if (WID == 5 && Q == 12) {
+            const int mb = k1_minb_override();
+            if (mb == 2) return launch_gather_gs<5, 16, 192, 2>(ctx, A, N, anchors, order, s);
+            if (mb == 4) return launch_gather_gs<5, 16, 192, 4>(ctx, A, N, anchors, order, s);
+            if (mb == 3) return launch_gather_gs<5, 16, 192, 3>(ctx, A, N, anchors, order, s);
+            return launch_gather_gs<5, 16, 192, 4>(ctx, A, N, anchors, order, s);
+        }
+        return launch_gather_gs<WID, 16, 0>(ctx, A, N, anchors, order, s);
+    }
+    if (WID == 5 && Q == 32) return launch_gather_gs<WID, 32, 512>(ctx, A, N, anchors, order, s);
+    if (WID == 5 && Q == 64) return launch_gather_gs<WID, 32, 1024>(ctx, A, N, anchors, order, s);
+    return launch_gather_gs<WID, 32, 0>(ctx, A, N, anchors, order, s);
 }
 
 int mvs_launch_score_refexact(mvs_ctx* ctx, int64_t N, const double* c, const int32_t* ref, double thr, int wid,
@@ -381,16 +512,21 @@ int mvs_launch_score_refexact(mvs_ctx* ctx, int64_t N, const double* c, const in
     if ((rc = mvs_bin_hypotheses(ctx, N, c, ref, wid, sort, vis, avg, count, xy, ncc, s)) != MVS_OK) return rc;
     const uint32_t* anchors = sort ? ctx->d_bin_sanchor : ctx->d_bin_anchor;
     const int32_t* order = sort ? ctx->d_bin_order : nullptr;
+    ScoreArgs A;
+    A.gray4 = ctx->d_gray; A.smap = ctx->d_smap; A.vmap = ctx->d_vmap;
+    A.V = ctx->V; A.Vp = ctx->Vp; A.Q = ctx->Q; A.W = ctx->W;
+    A.gstride = ctx->gstride; A.rowpitch = ctx->rowpitch;
+    A.ref = ref; A.thr = thr; A.vis_out = vis; A.avg_out = avg; A.count_out = count; A.ncc_out = ncc;
     const int pslot = (int)(ctx->prof_n % MVS_PROF_RING);
     if (ctx->profile) MVS_CUDA_CHECK(cudaEventRecord(ctx->prof_ev[2 * pslot], s));
     switch (wid) {
-        case 1: rc = launch_gather<1>(ctx, N, anchors, order, ref, thr, vis, avg, count, ncc, s); break;
-        case 2: rc = launch_gather<2>(ctx, N, anchors, order, ref, thr, vis, avg, count, ncc, s); break;
-        case 3: rc = launch_gather<3>(ctx, N, anchors, order, ref, thr, vis, avg, count, ncc, s); break;
-        case 4: rc = launch_gather<4>(ctx, N, anchors, order, ref, thr, vis, avg, count, ncc, s); break;
-        case 5: rc = launch_gather<5>(ctx, N, anchors, order, ref, thr, vis, avg, count, ncc, s); break;
-        case 6: rc = launch_gather<6>(ctx, N, anchors, order, ref, thr, vis, avg, count, ncc, s); break;
-        default: rc = launch_gather<7>(ctx, N, anchors, order, ref, thr, vis, avg, count, ncc, s); break;
+        case 1: rc = launch_gather<1>(ctx, A, N, anchors, order, s); break;
+        case 2: rc = launch_gather<2>(ctx, A, N, anchors, order, s); break;
+        case 3: rc = launch_gather<3>(ctx, A, N, anchors, order, s); break;
+        case 4: rc = launch_gather<4>(ctx, A, N, anchors, order, s); break;
+        case 5: rc = launch_gather<5>(ctx, A, N, anchors, order, s); break;
+        case 6: rc = launch_gather<6>(ctx, A, N, anchors, order, s); break;
+        default: rc = launch_gather<7>(ctx, A, N, anchors, order, s); break;
     }
     if (ctx->profile) {
         MVS_CUDA_CHECK(cudaEventRecord(ctx->prof_ev[2 * pslot + 1], s));
