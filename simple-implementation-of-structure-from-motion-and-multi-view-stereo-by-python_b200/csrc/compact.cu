@@ -7,7 +7,8 @@
 // set.  Output order = input order (ascending global index), so the result does not
 // depend on how the batch was sharded across GPUs.
 //
-// Three small launches: per-tile counts, one-block exclusive scan, scatter.
+// Three small launches: per-tile counts, one-block exclusive scan, scatter (records are
+// staged in shared memory and written out coalesced).
 // HBM-bound; algorithmic bytes = 4 B/hypothesis read + record_bytes per accepted.
 #include "mvs_common.cuh"
 
@@ -72,16 +73,20 @@ __global__ void __launch_bounds__(1024) compact_scan(int32_t* __restrict__ tile_
     if (threadIdx.x == 0) *n_out = carry;
 }
 
+// Records are assembled in shared memory (a kept hypothesis writes its own record there) and
+// then streamed out as one contiguous, coalesced run of 8-byte words per 256 hypotheses.
 __global__ void __launch_bounds__(256)
     compact_scatter(const int32_t* __restrict__ count, const uint8_t* __restrict__ gate, int bound, int64_t N,
                     const int32_t* __restrict__ tile_offsets, int64_t index_base, const double* __restrict__ c,
                     const double* __restrict__ nrm, const int32_t* __restrict__ ref, const uint64_t* __restrict__ vis,
                     const double* __restrict__ avg, const double* __restrict__ xy, int mw, uint8_t* __restrict__ records,
                     int rec_bytes, int64_t capacity, const int64_t* __restrict__ index_arr, const int32_t* __restrict__ px) {
+    extern __shared__ __align__(16) uint8_t s_rec[];       // 256 records
     __shared__ int warp_base[8];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t base = (int64_t)blockIdx.x * TILE;
     int64_t out = tile_offsets[blockIdx.x];
+    const int rec_words = rec_bytes >> 3;
     for (int j = 0; j < 4; ++j) {
         const int64_t i = base + j * 256 + threadIdx.x;
         const bool k = keep_flag(count, gate, bound, i, N);
@@ -94,23 +99,30 @@ __global__ void __launch_bounds__(256)
             total += warp_base[q];
         }
         if (k) {
-            const int64_t dst = out + before + __popc(b & ((1u << lane) - 1u));
-            if (dst < capacity) {
-                mvs_patch_record* r = reinterpret_cast<mvs_patch_record*>(records + dst * rec_bytes);
-                r->c[0] = c[3 * i]; r->c[1] = c[3 * i + 1]; r->c[2] = c[3 * i + 2];
-                if (nrm) { r->n[0] = nrm[3 * i]; r->n[1] = nrm[3 * i + 1]; r->n[2] = nrm[3 * i + 2]; }
-                else { r->n[0] = r->n[1] = r->n[2] = 0.0; }
-                r->xy[0] = xy[2 * i]; r->xy[1] = xy[2 * i + 1];
-                r->avg = avg[i];
-                r->ref = ref[i];
-                r->count = count[i];
-                r->index = index_arr ? index_arr[i] : index_base + i;
-                r->px[0] = px ? px[2 * i] : -1;
-                r->px[1] = px ? px[2 * i + 1] : -1;
-                uint64_t* rv = reinterpret_cast<uint64_t*>(r + 1);
-                for (int q = 0; q < mw; ++q) rv[q] = vis[i * mw + q];
-            }
+            const int slot = before + __popc(b & ((1u << lane) - 1u));
+            mvs_patch_record* r = reinterpret_cast<mvs_patch_record*>(s_rec + (size_t)slot * rec_bytes);
+            r->c[0] = c[3 * i]; r->c[1] = c[3 * i + 1]; r->c[2] = c[3 * i + 2];
+            if (nrm) { r->n[0] = nrm[3 * i]; r->n[1] = nrm[3 * i + 1]; r->n[2] = nrm[3 * i + 2]; }
+            else { r->n[0] = r->n[1] = r->n[2] = 0.0; }
+            r->xy[0] = xy[2 * i]; r->xy[1] = xy[2 * i + 1];
+            r->avg = avg[i];
+            r->ref = ref[i];
+            r->count = count[i];
+            r->index = index_arr ? index_arr[i] : index_base + i;
+            r->px[0] = px ? px[2 * i] : -1;
+            r->px[1] = px ? px[2 * i + 1] : -1;
+            uint64_t* rv = reinterpret_cast<uint64_t*>(r + 1);
+            for (int q = 0; q < mw; ++q) rv[q] = vis[i * mw + q];
         }
+        __syncthreads();
+        // records beyond `capacity` are counted but not written
+        int64_t room = capacity - out;
+        room = room < 0 ? 0 : room;
+        const int nrec = (int)(room < total ? room : total);
+        const int nwords = nrec * rec_words;
+        uint64_t* dst = reinterpret_cast<uint64_t*>(records + out * rec_bytes);
+        const uint64_t* src = reinterpret_cast<const uint64_t*>(s_rec);
+        for (int t = threadIdx.x; t < nwords; t += 256) dst[t] = src[t];
         out += total;
         __syncthreads();
     }
@@ -140,8 +152,12 @@ int mvs_launch_compact(mvs_ctx* ctx, int64_t N, int64_t index_base, const double
     }
     compact_count<<<T, 256, 0, s>>>(count, gate, bound, N, ctx->d_tiles);
     compact_scan<<<1, 1024, 0, s>>>(ctx->d_tiles, T, d_n_out);
-    compact_scatter<<<T, 256, 0, s>>>(count, gate, bound, N, ctx->d_tiles, index_base, c, nrm, ref, vis, avg, xy, mw,
-                                      (uint8_t*)records, (int)(sizeof(mvs_patch_record) + 8 * mw), capacity, index_arr, px);
+    const int rec_bytes = (int)(sizeof(mvs_patch_record) + 8 * mw);
+    const size_t smem = (size_t)256 * rec_bytes;
+    if (smem > 48 * 1024)
+        MVS_CUDA_CHECK(cudaFuncSetAttribute(compact_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    compact_scatter<<<T, 256, smem, s>>>(count, gate, bound, N, ctx->d_tiles, index_base, c, nrm, ref, vis, avg, xy, mw,
+                                         (uint8_t*)records, rec_bytes, capacity, index_arr, px);
     ctx->launches += 3;
     MVS_CUDA_CHECK(cudaGetLastError());
     return MVS_OK;

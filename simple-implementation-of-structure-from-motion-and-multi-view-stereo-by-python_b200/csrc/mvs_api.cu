@@ -238,6 +238,13 @@ extern "C" int mvs_destroy(mvs_ctx* ctx) {
         if (b) cudaFree(b);
     for (int i = 0; i < 2 * MVS_PROF_RING; ++i)
         if (ctx->prof_ev[i]) cudaEventDestroy(ctx->prof_ev[i]);
+    if (ctx->in_stream) cudaStreamDestroy(ctx->in_stream);
+    if (ctx->out_stream) cudaStreamDestroy(ctx->out_stream);
+    for (int i = 0; i < 3; ++i) {
+        if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
+        if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
+        if (ctx->ev_out[i]) cudaEventDestroy(ctx->ev_out[i]);
+    }
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     free(ctx->h_rrt);
     free(ctx->h_centres);
@@ -331,32 +338,61 @@ extern "C" int mvs_score_batch(mvs_ctx* ctx, int mode, int64_t N, const double* 
     if (on_device) {
         return mvs_launch_score_refexact(ctx, N, c, ref, min_ncc, wid, vis_mask, avg, count, xy, ncc, (cudaStream_t)stream);
     }
-    // host mode: stage in, run, stage out, synchronise
-    const size_t b_c = align256(sizeof(double) * 3 * N), b_ref = align256(sizeof(int32_t) * N);
-    const size_t b_vis = align256(sizeof(uint64_t) * mw * N), b_avg = align256(sizeof(double) * N);
-    const size_t b_cnt = align256(sizeof(int32_t) * N), b_xy = align256(sizeof(double) * 2 * N);
-    const size_t b_ncc = ncc ? align256(sizeof(float) * (size_t)V * N) : 0;
-    int rc = ensure_stage(ctx, b_c + b_ref + b_vis + b_avg + b_cnt + b_xy + b_ncc);
+    // host mode: a three-stage pipeline over chunks of the batch -- H2D of chunk k+1, the kernels of
+    // chunk k and D2H of chunk k-1 run concurrently on three streams (PCIe is full duplex), three
+    // staging slots.  Synchronises before returning.
+    const int64_t CH = N > (1 << 18) ? (1 << 17) : N;       // hypotheses per chunk
+    const size_t b_c = align256(sizeof(double) * 3 * CH), b_ref = align256(sizeof(int32_t) * CH);
+    const size_t b_vis = align256(sizeof(uint64_t) * mw * CH), b_avg = align256(sizeof(double) * CH);
+    const size_t b_cnt = align256(sizeof(int32_t) * CH), b_xy = align256(sizeof(double) * 2 * CH);
+    const size_t b_ncc = ncc ? align256(sizeof(float) * (size_t)V * CH) : 0;
+    const size_t slot = b_c + b_ref + b_vis + b_avg + b_cnt + b_xy + b_ncc;
+    const int nslots = N > CH ? 3 : 1;
+    int rc = ensure_stage(ctx, slot * nslots);
     if (rc != MVS_OK) return rc;
-    cudaStream_t s = ctx->own_stream;
-    uint8_t* p = (uint8_t*)ctx->d_stage;
-    double* d_c = (double*)p; p += b_c;
-    int32_t* d_ref = (int32_t*)p; p += b_ref;
-    uint64_t* d_vis = (uint64_t*)p; p += b_vis;
-    double* d_avg = (double*)p; p += b_avg;
-    int32_t* d_cnt = (int32_t*)p; p += b_cnt;
-    double* d_xy = (double*)p; p += b_xy;
-    float* d_ncc = ncc ? (float*)p : nullptr;
-    MVS_CUDA_CHECK(cudaMemcpyAsync(d_c, c, sizeof(double) * 3 * N, cudaMemcpyHostToDevice, s));
-    MVS_CUDA_CHECK(cudaMemcpyAsync(d_ref, ref, sizeof(int32_t) * N, cudaMemcpyHostToDevice, s));
-    rc = mvs_launch_score_refexact(ctx, N, d_c, d_ref, min_ncc, wid, d_vis, d_avg, d_cnt, d_xy, d_ncc, s);
-    if (rc != MVS_OK) return rc;
-    MVS_CUDA_CHECK(cudaMemcpyAsync(vis_mask, d_vis, sizeof(uint64_t) * mw * N, cudaMemcpyDeviceToHost, s));
-    MVS_CUDA_CHECK(cudaMemcpyAsync(count, d_cnt, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, s));
-    if (avg) MVS_CUDA_CHECK(cudaMemcpyAsync(avg, d_avg, sizeof(double) * N, cudaMemcpyDeviceToHost, s));
-    if (xy) MVS_CUDA_CHECK(cudaMemcpyAsync(xy, d_xy, sizeof(double) * 2 * N, cudaMemcpyDeviceToHost, s));
-    if (ncc) MVS_CUDA_CHECK(cudaMemcpyAsync(ncc, d_ncc, sizeof(float) * (size_t)V * N, cudaMemcpyDeviceToHost, s));
-    MVS_CUDA_CHECK(cudaStreamSynchronize(s));
+    if (!ctx->in_stream) {
+        MVS_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->in_stream, cudaStreamNonBlocking));
+        MVS_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->out_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 3; ++i) {
+            MVS_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
+            MVS_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming));
+            MVS_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_out[i], cudaEventDisableTiming));
+        }
+    }
+    // window maps first, so that the first chunk's kernels do not wait behind their build
+    if ((rc = mvs_build_window_maps(ctx, wid, ctx->own_stream)) != MVS_OK) return rc;
+    int64_t k = 0;
+    for (int64_t lo = 0; lo < N; lo += CH, ++k) {
+        const int64_t n = (N - lo < CH) ? (N - lo) : CH;
+        const int sl = (int)(k % nslots);
+        uint8_t* p = (uint8_t*)ctx->d_stage + slot * sl;
+        double* d_c = (double*)p; p += b_c;
+        int32_t* d_ref = (int32_t*)p; p += b_ref;
+        uint64_t* d_vis = (uint64_t*)p; p += b_vis;
+        double* d_avg = (double*)p; p += b_avg;
+        int32_t* d_cnt = (int32_t*)p; p += b_cnt;
+        double* d_xy = (double*)p; p += b_xy;
+        float* d_ncc = ncc ? (float*)p : nullptr;
+        // slot reuse: chunk k-3's results must have left the slot
+        if (k >= nslots) MVS_CUDA_CHECK(cudaStreamWaitEvent(ctx->in_stream, ctx->ev_out[sl], 0));
+        MVS_CUDA_CHECK(cudaMemcpyAsync(d_c, c + 3 * lo, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, ctx->in_stream));
+        MVS_CUDA_CHECK(cudaMemcpyAsync(d_ref, ref + lo, sizeof(int32_t) * n, cudaMemcpyHostToDevice, ctx->in_stream));
+        MVS_CUDA_CHECK(cudaEventRecord(ctx->ev_in[sl], ctx->in_stream));
+        MVS_CUDA_CHECK(cudaStreamWaitEvent(ctx->own_stream, ctx->ev_in[sl], 0));
+        rc = mvs_launch_score_refexact(ctx, n, d_c, d_ref, min_ncc, wid, d_vis, d_avg, d_cnt, d_xy, d_ncc, ctx->own_stream);
+        if (rc != MVS_OK) return rc;
+        MVS_CUDA_CHECK(cudaEventRecord(ctx->ev_done[sl], ctx->own_stream));
+        MVS_CUDA_CHECK(cudaStreamWaitEvent(ctx->out_stream, ctx->ev_done[sl], 0));
+        cudaStream_t so = ctx->out_stream;
+        MVS_CUDA_CHECK(cudaMemcpyAsync(vis_mask + mw * lo, d_vis, sizeof(uint64_t) * mw * n, cudaMemcpyDeviceToHost, so));
+        MVS_CUDA_CHECK(cudaMemcpyAsync(count + lo, d_cnt, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, so));
+        if (avg) MVS_CUDA_CHECK(cudaMemcpyAsync(avg + lo, d_avg, sizeof(double) * n, cudaMemcpyDeviceToHost, so));
+        if (xy) MVS_CUDA_CHECK(cudaMemcpyAsync(xy + 2 * lo, d_xy, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost, so));
+        if (ncc) MVS_CUDA_CHECK(cudaMemcpyAsync(ncc + (size_t)V * lo, d_ncc, sizeof(float) * (size_t)V * n, cudaMemcpyDeviceToHost, so));
+        MVS_CUDA_CHECK(cudaEventRecord(ctx->ev_out[sl], so));
+    }
+    MVS_CUDA_CHECK(cudaStreamSynchronize(ctx->out_stream));
+    MVS_CUDA_CHECK(cudaStreamSynchronize(ctx->own_stream));
     return MVS_OK;
 }
 

@@ -74,6 +74,10 @@ struct mvs_ctx {
     void* d_stage;
     size_t stage_bytes;
     cudaStream_t own_stream;
+    // host-mode pipeline (mvs_score_batch with host buffers): copy-in / compute / copy-out streams,
+    // three staging slots
+    cudaStream_t in_stream, out_stream;
+    cudaEvent_t ev_in[3], ev_done[3], ev_out[3];
     // compaction scratch
     int32_t* d_tiles;
     size_t tile_bytes;
