@@ -40,6 +40,12 @@ extern "C" {
 #define MVS_MODE_REFEXACT 0 /* "Mode A": literal behaviour of MVS2.py:62-77 */
 #define MVS_MODE_PMVS 1     /* "Mode B": per-view projection, oriented mu x mu bilinear grid */
 
+/* flags for mvs_score_pmvs */
+#define MVS_PMVS_REDUCE_TO_REFEXACT 1 /* collapse Mode B onto the reference's behaviour: the reference
+                                         camera for every view (MVS2.py:68), image-aligned integer lattice
+                                         around (int(x), int(y)), no interpolation, the bounds rule of
+                                         HarrisFeatures.py:128 -- must agree with MVS_MODE_REFEXACT */
+
 typedef struct mvs_ctx mvs_ctx;
 
 /* ABI version of this header (checked by the Python loader). */
@@ -106,6 +112,36 @@ int mvs_get_cameras(const mvs_ctx* ctx, double* Rrt_host, double* centres_host);
 int mvs_score_batch(mvs_ctx* ctx, int mode, int64_t N, const double* c, const double* nrm, const int32_t* ref,
                     double min_ncc, int wid, uint64_t* vis_mask, double* avg, int32_t* count, double* xy, float* ncc,
                     int on_device, void* stream);
+
+/*
+ * Mode B ("PMVS-style") scoring with optional on-chip selection over hypothesis sets.
+ * Replaces: nothing in the reference -- MVS2.py:62-77 never projects into the other views,
+ *           never interpolates and never reads patch.n.  This is the scorer
+ *           BASELINE.json's north_star describes; its normative spec is oracle/mode_b.py
+ *           and it is reported as an extension.  Same outputs as mvs_score_batch.
+ *   c, nrm, ref   as mvs_score_batch (nrm required unless MVS_PMVS_REDUCE_TO_REFEXACT)
+ *   cand [N, ceil(V/64)] optional candidate-view mask (NULL = every view)
+ *   mu        grid size (3, 5, 7, 9 or 11): mu x mu samples, one grid step ~ one pixel in
+ *             the reference view, every view sampled bilinearly through ITS OWN camera
+ *   group     > 1: hypotheses [s*group, (s+1)*group) form selection set s (e.g. the depth x
+ *             normal variants of one cell); best_idx[s] = index inside the set of the member
+ *             with the highest avg among those with count >= bound (lowest index on ties,
+ *             -1 when none), best_avg[s] = its avg.  The per-hypothesis outputs (vis_mask,
+ *             avg, count, xy, ncc) may then all be NULL: only one record per set leaves the SM.
+ *   best_idx [ceil(N/group)] int32, best_avg [ceil(N/group)] float64 (either may be NULL)
+ */
+int mvs_score_pmvs(mvs_ctx* ctx, int64_t N, const double* c, const double* nrm, const int32_t* ref,
+                   const uint64_t* cand, double min_ncc, int mu, int flags, int group, int bound, uint64_t* vis_mask,
+                   double* avg, int32_t* count, double* xy, float* ncc, int32_t* best_idx, double* best_avg,
+                   int on_device, void* stream);
+
+/*
+ * Selection over hypothesis sets for an already scored batch of either mode (SURVEY appendix
+ * A.7; the reference has no refinement/argmax step -- north_star extension): same rule as the
+ * `group` argument of mvs_score_pmvs.  DEVICE pointers; enqueued on `stream`.
+ */
+int mvs_select_best(mvs_ctx* ctx, int64_t N, int group, const double* avg, const int32_t* count, int bound,
+                    int32_t* best_idx, double* best_avg, void* stream);
 
 /*
  * One accepted patch as exchanged between GPUs after a round: the fields of the

@@ -13,6 +13,7 @@ from . import _lib
 
 MODE_REFEXACT = 0
 MODE_PMVS = 1
+PMVS_REDUCE_TO_REFEXACT = 1
 
 
 class MvsError(Exception):
@@ -172,3 +173,75 @@ class MvsContext:
                                            p(out.get("ncc")), 1, C.c_void_p(stream)),
                "mvs_score_batch")
         return out
+
+    # -- Mode B (north_star extension; spec = oracle/mode_b.py) --------------------------
+    def score_pmvs_host(self, c, nrm, ref, min_ncc=0.7, mu=5, cand=None, flags=0, group=0, bound=3, want_ncc=False,
+                        per_hypothesis=True):
+        """Mode B through host buffers.  Returns the dict of score_host plus, when group > 1,
+        best_idx [ceil(N/group)] i32 and best_avg f64; per_hypothesis=False skips every
+        per-hypothesis output (only one record per selection set leaves the device)."""
+        c = np.ascontiguousarray(np.asarray(c, dtype=np.float64).reshape(-1, 3))
+        N = c.shape[0]
+        ref = np.ascontiguousarray(np.asarray(ref, dtype=np.int32).reshape(-1))
+        if nrm is not None:
+            nrm = np.ascontiguousarray(np.asarray(nrm, dtype=np.float64).reshape(-1, 3))
+        mw = mask_words(self.V)
+        if cand is not None:
+            cand = np.ascontiguousarray(np.asarray(cand, dtype=np.uint64).reshape(N, mw))
+        out = {}
+        if per_hypothesis:
+            out = dict(vis_mask=np.zeros((N, mw), np.uint64), avg=np.zeros(N), count=np.zeros(N, np.int32),
+                       xy=np.zeros((N, 2)))
+            if want_ncc:
+                out["ncc"] = np.empty((N, self.V), np.float32)
+        if group > 1:
+            ns = (N + group - 1) // group
+            out["best_idx"] = np.full(ns, -2, np.int32)
+            out["best_avg"] = np.zeros(ns)
+        g = out.get
+        _check(_lib.load().mvs_score_pmvs(self._h, N, _np_ptr(c), _np_ptr(nrm), _np_ptr(ref), _np_ptr(cand), float(min_ncc),
+                                          int(mu), int(flags), int(group), int(bound), _np_ptr(g("vis_mask")),
+                                          _np_ptr(g("avg")), _np_ptr(g("count")), _np_ptr(g("xy")), _np_ptr(g("ncc")),
+                                          _np_ptr(g("best_idx")), _np_ptr(g("best_avg")), 0, None), "mvs_score_pmvs")
+        return out
+
+    def score_pmvs_device(self, c, nrm, ref, min_ncc=0.7, mu=5, cand=None, flags=0, group=0, bound=3, out=None,
+                          per_hypothesis=True, stream=None):
+        """Mode B on device tensors (c, nrm [N,3] f64, ref [N] i32, cand [N,mw] i64); enqueues only."""
+        import torch
+        N = c.shape[0]
+        dev = c.device
+        mw = mask_words(self.V)
+        out = {} if out is None else out
+        if per_hypothesis:
+            out.setdefault("vis_mask", torch.empty((N, mw), dtype=torch.int64, device=dev))
+            out.setdefault("avg", torch.empty(N, dtype=torch.float64, device=dev))
+            out.setdefault("count", torch.empty(N, dtype=torch.int32, device=dev))
+            out.setdefault("xy", torch.empty((N, 2), dtype=torch.float64, device=dev))
+        if group > 1:
+            ns = (N + group - 1) // group
+            out.setdefault("best_idx", torch.empty(ns, dtype=torch.int32, device=dev))
+            out.setdefault("best_avg", torch.empty(ns, dtype=torch.float64, device=dev))
+        if stream is None:
+            stream = torch.cuda.current_stream(dev).cuda_stream
+        p = lambda x: C.c_void_p(x.data_ptr()) if x is not None else None
+        g = out.get
+        _check(_lib.load().mvs_score_pmvs(self._h, N, p(c), p(nrm), p(ref), p(cand), float(min_ncc), int(mu), int(flags),
+                                          int(group), int(bound), p(g("vis_mask")), p(g("avg")), p(g("count")),
+                                          p(g("xy")), p(g("ncc")), p(g("best_idx")), p(g("best_avg")), 1,
+                                          C.c_void_p(stream)), "mvs_score_pmvs")
+        return out
+
+    def select_best_device(self, avg, count, group, bound=3, stream=None):
+        """Argmax over consecutive sets of an already scored device batch -> (best_idx i32, best_avg f64)."""
+        import torch
+        N = avg.shape[0]
+        ns = (N + group - 1) // group
+        bi = torch.empty(ns, dtype=torch.int32, device=avg.device)
+        ba = torch.empty(ns, dtype=torch.float64, device=avg.device)
+        if stream is None:
+            stream = torch.cuda.current_stream(avg.device).cuda_stream
+        _check(_lib.load().mvs_select_best(self._h, N, int(group), C.c_void_p(avg.data_ptr()), C.c_void_p(count.data_ptr()),
+                                           int(bound), C.c_void_p(bi.data_ptr()), C.c_void_p(ba.data_ptr()),
+                                           C.c_void_p(stream)), "mvs_select_best")
+        return bi, ba

@@ -227,6 +227,7 @@ extern "C" int mvs_destroy(mvs_ctx* ctx) {
     if (ctx->d_geom) cudaFree(ctx->d_geom);
     if (ctx->d_stage) cudaFree(ctx->d_stage);
     if (ctx->d_tiles) cudaFree(ctx->d_tiles);
+    mvs_pmvs_release(ctx);
     void* more[] = {ctx->d_smap, ctx->d_vmap, ctx->d_bin_hist, ctx->d_bin_key, ctx->d_bin_rank, ctx->d_bin_order,
                     ctx->d_bin_anchor, ctx->d_bin_sanchor, ctx->d_bin_scan};
     for (void* b : more)
@@ -325,8 +326,11 @@ extern "C" int mvs_score_batch(mvs_ctx* ctx, int mode, int64_t N, const double* 
         mvs_set_error("mvs_score_batch: c, ref, vis_mask and count are required");
         return MVS_ERR_ARG;
     }
+    if (mode == MVS_MODE_PMVS)
+        return mvs_score_pmvs(ctx, N, c, nrm, ref, nullptr, min_ncc, 2 * wid + 1, 0, 0, 0, vis_mask, avg, count, xy, ncc,
+                              nullptr, nullptr, on_device, stream);
     if (mode != MVS_MODE_REFEXACT) {
-        mvs_set_error("mvs_score_batch: mode %d is not available in this build", mode);
+        mvs_set_error("mvs_score_batch: unknown mode %d", mode);
         return MVS_ERR_ARG;
     }
     if (wid < 1 || wid > 7) { mvs_set_error("mvs_score_batch: wid must be in 1..7 (got %d)", wid); return MVS_ERR_ARG; }
@@ -394,6 +398,86 @@ extern "C" int mvs_score_batch(mvs_ctx* ctx, int mode, int64_t N, const double* 
     MVS_CUDA_CHECK(cudaStreamSynchronize(ctx->out_stream));
     MVS_CUDA_CHECK(cudaStreamSynchronize(ctx->own_stream));
     return MVS_OK;
+}
+
+extern "C" int mvs_score_pmvs(mvs_ctx* ctx, int64_t N, const double* c, const double* nrm, const int32_t* ref,
+                              const uint64_t* cand, double min_ncc, int mu, int flags, int group, int bound,
+                              uint64_t* vis_mask, double* avg, int32_t* count, double* xy, float* ncc, int32_t* best_idx,
+                              double* best_avg, int on_device, void* stream) {
+    if (!ctx) { mvs_set_error("mvs_score_pmvs: null context"); return MVS_ERR_ARG; }
+    const bool reduce = (flags & MVS_PMVS_REDUCE_TO_REFEXACT) != 0;
+    if (N < 0 || (N > 0 && (!c || !ref || (!nrm && !reduce)))) {
+        mvs_set_error("mvs_score_pmvs: c, ref and (unless reducing to Mode A) nrm are required");
+        return MVS_ERR_ARG;
+    }
+    if (mu != 3 && mu != 5 && mu != 7 && mu != 9 && mu != 11) {
+        mvs_set_error("mvs_score_pmvs: mu must be 3, 5, 7, 9 or 11 (got %d)", mu);
+        return MVS_ERR_ARG;
+    }
+    if (group > 1 && !best_idx) { mvs_set_error("mvs_score_pmvs: best_idx is required when group > 1"); return MVS_ERR_ARG; }
+    if (group <= 1 && (!vis_mask || !count)) {
+        mvs_set_error("mvs_score_pmvs: vis_mask and count are required without selection");
+        return MVS_ERR_ARG;
+    }
+    if (N == 0) return MVS_OK;
+    MVS_CUDA_CHECK(cudaSetDevice(ctx->device));
+    if (on_device)
+        return mvs_launch_score_pmvs(ctx, N, c, nrm, ref, cand, min_ncc, mu, flags, group, bound, vis_mask, avg, count, xy,
+                                     ncc, best_idx, best_avg, (cudaStream_t)stream);
+    // host mode: stage in, run, stage out, synchronise
+    const int V = ctx->V;
+    const size_t mw = (size_t)((V + 63) / 64);
+    const int g = group > 1 ? group : 1;
+    const int64_t n_sets = (N + g - 1) / g;
+    const size_t b_c = align256(sizeof(double) * 3 * N), b_n = nrm ? b_c : 0, b_ref = align256(sizeof(int32_t) * N);
+    const size_t b_cand = cand ? align256(sizeof(uint64_t) * mw * N) : 0;
+    const size_t b_vis = vis_mask ? align256(sizeof(uint64_t) * mw * N) : 0, b_avg = avg ? align256(sizeof(double) * N) : 0;
+    const size_t b_cnt = count ? align256(sizeof(int32_t) * N) : 0, b_xy = xy ? align256(sizeof(double) * 2 * N) : 0;
+    const size_t b_ncc = ncc ? align256(sizeof(float) * (size_t)V * N) : 0;
+    const size_t b_bi = best_idx ? align256(sizeof(int32_t) * n_sets) : 0, b_ba = best_avg ? align256(sizeof(double) * n_sets) : 0;
+    int rc = ensure_stage(ctx, b_c + b_n + b_ref + b_cand + b_vis + b_avg + b_cnt + b_xy + b_ncc + b_bi + b_ba);
+    if (rc != MVS_OK) return rc;
+    cudaStream_t s = ctx->own_stream;
+    uint8_t* p = (uint8_t*)ctx->d_stage;
+    auto take = [&](size_t bytes) -> void* { void* q = bytes ? (void*)p : nullptr; p += bytes; return q; };
+    double* d_c = (double*)take(b_c);
+    double* d_n = (double*)take(b_n);
+    int32_t* d_ref = (int32_t*)take(b_ref);
+    uint64_t* d_cand = (uint64_t*)take(b_cand);
+    uint64_t* d_vis = (uint64_t*)take(b_vis);
+    double* d_avg = (double*)take(b_avg);
+    int32_t* d_cnt = (int32_t*)take(b_cnt);
+    double* d_xy = (double*)take(b_xy);
+    float* d_ncc = (float*)take(b_ncc);
+    int32_t* d_bi = (int32_t*)take(b_bi);
+    double* d_ba = (double*)take(b_ba);
+    MVS_CUDA_CHECK(cudaMemcpyAsync(d_c, c, sizeof(double) * 3 * N, cudaMemcpyHostToDevice, s));
+    if (nrm) MVS_CUDA_CHECK(cudaMemcpyAsync(d_n, nrm, sizeof(double) * 3 * N, cudaMemcpyHostToDevice, s));
+    MVS_CUDA_CHECK(cudaMemcpyAsync(d_ref, ref, sizeof(int32_t) * N, cudaMemcpyHostToDevice, s));
+    if (cand) MVS_CUDA_CHECK(cudaMemcpyAsync(d_cand, cand, sizeof(uint64_t) * mw * N, cudaMemcpyHostToDevice, s));
+    rc = mvs_launch_score_pmvs(ctx, N, d_c, d_n, d_ref, d_cand, min_ncc, mu, flags, group, bound, d_vis, d_avg, d_cnt, d_xy,
+                               d_ncc, d_bi, d_ba, s);
+    if (rc != MVS_OK) return rc;
+    if (vis_mask) MVS_CUDA_CHECK(cudaMemcpyAsync(vis_mask, d_vis, sizeof(uint64_t) * mw * N, cudaMemcpyDeviceToHost, s));
+    if (count) MVS_CUDA_CHECK(cudaMemcpyAsync(count, d_cnt, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, s));
+    if (avg) MVS_CUDA_CHECK(cudaMemcpyAsync(avg, d_avg, sizeof(double) * N, cudaMemcpyDeviceToHost, s));
+    if (xy) MVS_CUDA_CHECK(cudaMemcpyAsync(xy, d_xy, sizeof(double) * 2 * N, cudaMemcpyDeviceToHost, s));
+    if (ncc) MVS_CUDA_CHECK(cudaMemcpyAsync(ncc, d_ncc, sizeof(float) * (size_t)V * N, cudaMemcpyDeviceToHost, s));
+    if (best_idx) MVS_CUDA_CHECK(cudaMemcpyAsync(best_idx, d_bi, sizeof(int32_t) * n_sets, cudaMemcpyDeviceToHost, s));
+    if (best_avg) MVS_CUDA_CHECK(cudaMemcpyAsync(best_avg, d_ba, sizeof(double) * n_sets, cudaMemcpyDeviceToHost, s));
+    MVS_CUDA_CHECK(cudaStreamSynchronize(s));
+    return MVS_OK;
+}
+
+extern "C" int mvs_select_best(mvs_ctx* ctx, int64_t N, int group, const double* avg, const int32_t* count, int bound,
+                               int32_t* best_idx, double* best_avg, void* stream) {
+    if (!ctx) { mvs_set_error("mvs_select_best: null context"); return MVS_ERR_ARG; }
+    if (N < 0 || group < 1 || (N > 0 && (!avg || !count || !best_idx))) {
+        mvs_set_error("mvs_select_best: need group >= 1 and avg, count, best_idx");
+        return MVS_ERR_ARG;
+    }
+    MVS_CUDA_CHECK(cudaSetDevice(ctx->device));
+    return mvs_launch_select_best(ctx, N, group, avg, count, bound, best_idx, best_avg, (cudaStream_t)stream);
 }
 
 extern "C" int mvs_record_bytes(const mvs_ctx* ctx) {

@@ -64,6 +64,12 @@ struct mvs_ctx {
     int profile;
     cudaEvent_t prof_ev[2 * MVS_PROF_RING];
     int64_t prof_n;       // scoring kernels bracketed since mvs_profile_enable(1)
+    // Mode B texture path (ncc_pmvs.cu), created on the first Mode B call
+    int pmvs_ready;
+    cudaArray_t* pmvs_arrays;              // [V] host table of 2-D gather-enabled arrays
+    cudaTextureObject_t* pmvs_tex_host;    // [V]
+    void* d_pmvs_tex;                      // [V] cudaTextureObject_t
+    void* d_pmvs_camf;                     // [V] CamProjF
     CamProj* d_cam;       // [V]
     CamGeom* d_geom;      // [V]
     double* h_rrt;        // [V,9] host copy
@@ -129,6 +135,13 @@ int mvs_build_window_maps(mvs_ctx* ctx, int wid, cudaStream_t s);
 // optionally order them by anchor tile; leaves anchors / order in ctx->d_bin_*
 int mvs_bin_hypotheses(mvs_ctx* ctx, int64_t N, const double* c, const int32_t* ref, int wid, bool sort, uint64_t* vis,
                        double* avg, int32_t* count, double* xy, float* ncc, cudaStream_t s);
+int mvs_launch_score_pmvs(mvs_ctx* ctx, int64_t N, const double* c, const double* nrm, const int32_t* ref,
+                          const uint64_t* cand, double thr, int mu, int flags, int group, int bound, uint64_t* vis,
+                          double* avg, int32_t* count, double* xy, float* ncc, int32_t* best_idx, double* best_avg,
+                          cudaStream_t s);
+int mvs_launch_select_best(mvs_ctx* ctx, int64_t N, int group, const double* avg, const int32_t* count, int bound,
+                           int32_t* best_idx, double* best_avg, cudaStream_t s);
+void mvs_pmvs_release(mvs_ctx* ctx);
 int mvs_launch_compact(mvs_ctx* ctx, int64_t N, int64_t index_base, const double* c, const double* nrm, const int32_t* ref,
                        const uint64_t* vis, const double* avg, const int32_t* count, const double* xy, const uint8_t* gate,
                        int bound, void* records, int64_t capacity, int64_t* d_n_out, const int64_t* index_arr,

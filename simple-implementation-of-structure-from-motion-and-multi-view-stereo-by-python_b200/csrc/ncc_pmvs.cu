@@ -1,0 +1,548 @@
+// K2 ncc_score_pmvs ("Mode B") for sm_100a: per-view projection, oriented mu x mu grid,
+// bilinear taps, mean multi-view NCC, on-chip argmax over hypothesis sets.
+//
+// This scorer does NOT exist in the reference (its MVS2.py:62-77 samples every view at the
+// reference camera's projection with a truncated window); it is the one BASELINE.json's
+// north_star describes and its normative spec is oracle/mode_b.py.  With
+// MVS_PMVS_REDUCE_TO_REFEXACT it collapses onto the reference's behaviour (same camera for
+// every view, image-aligned integer lattice, no interpolation, the bounds rule of
+// HarrisFeatures.py:128) and must then agree with K1.
+//
+// Hardware mapping: one warp per hypothesis (per hypothesis SET when selecting), lanes span
+// the mu*mu samples (ceil(mu^2/32) per lane).
+//   * per 16 views, lane v prepares view v: the projection of the patch centre through
+//     K_v (R'_v c + t_v) in fp64 and the per-step increments RELATIVE to it in fp32, staged in
+//     shared memory; a tap position is then 6 FMA + 1 reciprocal, accurate to ~1e-6 px;
+//   * the four bilinear taps of a sample come from ONE texture-gather instruction (tld4) on
+//     a per-view 2-D texture of the gray image (the texture path, not the LSU), as
+//     normalised floats; interpolation weights are exact fp32, not the sampler's 8-bit ones;
+//   * NCC sums are taken on pivot-shifted samples (x - x[lane 0]) so that low-variance
+//     windows keep full fp32 precision, and reduced across the warp with a transposing
+//     butterfly: 16 shuffles per quantity per 16 views instead of 5 per view;
+//   * the best hypothesis of a set (highest mean NCC among those with >= bound visible views,
+//     lowest index on ties) is tracked in registers and written once per set.
+// Tensor cores are not used: a gather-bound reduction has no dense contraction.
+#include "project.cuh"
+#include "scan.cuh"
+
+#define FULL 0xffffffffu
+#define PMVS_VAR_MIN (1e-3f / 65025.0f)        // oracle/mode_b.py VAR_MIN in (grey/255)^2
+
+// fp32 copy of one view's camera for the per-step increments
+struct __align__(16) CamProjF {
+    float r[9];
+    float fx, fy, cx, cy;
+    float pad[3];
+};
+
+struct PmvsArgs {
+    const CamProj* cams;
+    const CamProjF* camsf;
+    const cudaTextureObject_t* tex;
+    int V, H, W;
+    int flags;
+    int group;                 // hypotheses per selection set (<= 1: no selection)
+    int bound;
+    float thr;
+    const double* c;
+    const double* nrm;
+    const int32_t* ref;
+    const uint64_t* cand;      // optional [N, mw] candidate-view mask
+    uint64_t* vis_out;
+    double* avg_out;
+    int32_t* count_out;
+    double* xy_out;
+    float* ncc_out;
+    int32_t* best_idx;
+    double* best_avg;
+};
+
+// view-in-group index held by a lane after the transposing butterfly below
+__device__ __forceinline__ int lane_view16(int lane) {
+    return ((lane >> 4) & 1) + 8 * ((lane >> 3) & 1) + 4 * ((lane >> 2) & 1) + 2 * ((lane >> 1) & 1);
+}
+
+// Reduce 16 per-view partials across the warp: on return every lane holds the complete sum
+// of view lane_view16(lane).  16 shuffles.
+__device__ __forceinline__ float butterfly16f(const float (&a)[16], int lane) {
+    float b[8];
+    const bool h16 = lane & 16;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const float keep = h16 ? a[2 * q + 1] : a[2 * q];
+        const float send = h16 ? a[2 * q] : a[2 * q + 1];
+        b[q] = keep + __shfl_xor_sync(FULL, send, 16);
+    }
+    float c4[4];
+    const bool h8 = lane & 8;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float keep = h8 ? b[q + 4] : b[q];
+        const float send = h8 ? b[q] : b[q + 4];
+        c4[q] = keep + __shfl_xor_sync(FULL, send, 8);
+    }
+    float d2[2];
+    const bool h4 = lane & 4;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const float keep = h4 ? c4[q + 2] : c4[q];
+        const float send = h4 ? c4[q] : c4[q + 2];
+        d2[q] = keep + __shfl_xor_sync(FULL, send, 4);
+    }
+    const bool h2 = lane & 2;
+    const float keep = h2 ? d2[1] : d2[0];
+    const float send = h2 ? d2[0] : d2[1];
+    float e = keep + __shfl_xor_sync(FULL, send, 2);
+    e += __shfl_xor_sync(FULL, e, 1);
+    return e;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(FULL, v, s);
+    return v;
+}
+
+// One view's staged parameters.  A sample at grid offset (a, b) has homogeneous image
+// coordinates h0 + a*hx + b*hy; its pixel position is written RELATIVE to the projection
+// (uc, vc) of the patch centre, which the staging lane knows in fp64:
+//   u = uc + (a*gxu + b*gyu) / z,  gxu = hx.X - uc*hx.Z, ...,  z = Z0 + a*hxZ + b*hyZ
+// so fp32 only ever carries offsets of a few pixels (error ~1e-6 px instead of ~5e-5 px).
+// uc, vc are split into integer part and fraction.
+struct __align__(16) ViewAffine {
+    float iu, fu, iv, fv;
+    float Z0, hxZ, hyZ, gxu;
+    float gyu, gxv, gyv, pad;
+};
+
+// Bilinear sample through the gather path.  (u0, v0) = integer tap origin (pixel centres at
+// integers), (fu, fv) = fractions.  Returns the value in [0,1] and whether all four taps are
+// inside the image.
+__device__ __forceinline__ float tap4(cudaTextureObject_t tex, float u0, float v0, float fu, float fv, bool front, int W,
+                                      int H, bool& ok) {
+    ok = front && (u0 >= 0.0f) && (u0 <= (float)(W - 2)) && (v0 >= 0.0f) && (v0 <= (float)(H - 2));
+    // the footprint of a gather at (u0+1, v0+1) is texels (u0..u0+1, v0..v0+1); the centre of
+    // the 2x2 block is the robust coordinate.  Components: x=(0,1) y=(1,1) z=(1,0) w=(0,0) as
+    // (column offset, row offset).
+    const float4 g = tex2Dgather<float4>(tex, ok ? u0 + 1.0f : 1.0f, ok ? v0 + 1.0f : 1.0f, 0);
+    const float top = fmaf(fu, g.z - g.w, g.w);
+    const float bot = fmaf(fu, g.y - g.x, g.x);
+    return fmaf(fv, bot - top, top);
+}
+
+template <int MU>
+__global__ void __launch_bounds__(256, 2) ncc_score_pmvs(const PmvsArgs A, int64_t N) {
+    constexpr int NS = MU * MU;
+    constexpr int SPL = (NS + 31) / 32;                    // samples per lane
+    constexpr float HALF = 0.5f * (MU - 1);
+    __shared__ ViewAffine s_view[8][16];
+    __shared__ cudaTextureObject_t s_tex[8][16];
+
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int mw = (A.V + 63) >> 6;
+    const int group = A.group > 1 ? A.group : 1;
+    const int64_t n_sets = (N + group - 1) / group;
+    const float cn = (float)NS / (float)(NS - 1);
+    const bool reduce_a = (A.flags & MVS_PMVS_REDUCE_TO_REFEXACT) != 0;
+
+    // this lane's sample offsets on the grid (m = k*MU + j)
+    float aj[SPL], ak[SPL];
+    bool live[SPL];
+#pragma unroll
+    for (int q = 0; q < SPL; ++q) {
+        const int m = lane + 32 * q;
+        live[q] = m < NS;
+        const int mm = live[q] ? m : 0;
+        aj[q] = (float)(mm % MU) - HALF;
+        ak[q] = (float)(mm / MU) - HALF;
+    }
+
+    for (int64_t set = warp0; set < n_sets; set += nwarps) {
+        float best_key = -INFINITY;
+        int best_i = -1;
+        for (int gi = 0; gi < group; ++gi) {
+            const int64_t h = set * group + gi;
+            if (h >= N) break;
+            // ---- reference view: projection of the centre (fp64, cv2 order, as Mode A), patch axes
+            const int r = __ldg(A.ref + h);
+            const double c0 = __ldg(A.c + 3 * h), c1 = __ldg(A.c + 3 * h + 1), c2 = __ldg(A.c + 3 * h + 2);
+            double x = nan(""), y = nan("");
+            bool hyp_ok = (r >= 0) && (r < A.V);
+            float ex[3] = {0, 0, 0}, ey[3] = {0, 0, 0}, step = 0.0f;
+            int row = 0, col = 0;
+            if (hyp_ok) {
+                const CamProj& cr = A.cams[r];
+                project_ref(cr, c0, c1, c2, x, y);
+                const double Zc = cr.r[6] * c0 + cr.r[7] * c1 + cr.r[8] * c2 + cr.t[2];
+                if (reduce_a) {
+                    hyp_ok = window_anchor(x, y, A.H, A.W, (MU - 1) / 2, row, col);
+                } else {
+                    const float n0 = (float)__ldg(A.nrm + 3 * h), n1 = (float)__ldg(A.nrm + 3 * h + 1),
+                                n2 = (float)__ldg(A.nrm + 3 * h + 2);
+                    const float nn = sqrtf(n0 * n0 + n1 * n1 + n2 * n2);
+                    const float inn = 1.0f / nn;
+                    const float nh[3] = {n0 * inn, n1 * inn, n2 * inn};
+                    const float a0 = (float)cr.r[0], a1 = (float)cr.r[1], a2 = (float)cr.r[2];
+                    const float dn = a0 * nh[0] + a1 * nh[1] + a2 * nh[2];
+                    const float p0 = a0 - dn * nh[0], p1 = a1 - dn * nh[1], p2 = a2 - dn * nh[2];
+                    const float al = sqrtf(p0 * p0 + p1 * p1 + p2 * p2);
+                    const float ial = 1.0f / al;
+                    ex[0] = p0 * ial; ex[1] = p1 * ial; ex[2] = p2 * ial;
+                    ey[0] = ex[1] * nh[2] - ex[2] * nh[1];
+                    ey[1] = ex[2] * nh[0] - ex[0] * nh[2];
+                    ey[2] = ex[0] * nh[1] - ex[1] * nh[0];
+                    step = (float)(Zc / (0.5 * (cr.fx + cr.fy)));
+                    hyp_ok = isfinite(c0) && isfinite(c1) && isfinite(c2) && isfinite(nn) && (nn > 0.0f) && isfinite(Zc) &&
+                             (Zc > 0.0) && (al >= 1e-9f);
+                }
+            }
+            if (lane == 0 && A.xy_out) {
+                A.xy_out[2 * h] = x;
+                A.xy_out[2 * h + 1] = y;
+            }
+
+            // prepare view v for this hypothesis into slot `slot` (executed by one lane per view)
+            auto stage_view = [&](int v, int slot) {
+                const int cam = reduce_a ? r : v;          // MVS2.py:68: the reference camera for every view
+                const CamProj& cv = A.cams[cam];
+                const CamProjF& cf = A.camsf[cam];
+                const double Xc = cv.r[0] * c0 + cv.r[1] * c1 + cv.r[2] * c2 + cv.t[0];
+                const double Yc = cv.r[3] * c0 + cv.r[4] * c1 + cv.r[5] * c2 + cv.t[1];
+                const double Zv = cv.r[6] * c0 + cv.r[7] * c1 + cv.r[8] * c2 + cv.t[2];
+                ViewAffine va;
+                const double izd = 1.0 / Zv;
+                const double uc = (cv.fx * Xc + cv.cx * Zv) * izd, vc = (cv.fy * Yc + cv.cy * Zv) * izd;
+                const double ucf = floor(uc), vcf = floor(vc);
+                va.iu = (float)ucf; va.fu = (float)(uc - ucf);
+                va.iv = (float)vcf; va.fv = (float)(vc - vcf);
+                va.Z0 = (float)Zv;
+                const float rx0 = cf.r[0] * ex[0] + cf.r[1] * ex[1] + cf.r[2] * ex[2];
+                const float rx1 = cf.r[3] * ex[0] + cf.r[4] * ex[1] + cf.r[5] * ex[2];
+                const float rx2 = cf.r[6] * ex[0] + cf.r[7] * ex[1] + cf.r[8] * ex[2];
+                const float ry0 = cf.r[0] * ey[0] + cf.r[1] * ey[1] + cf.r[2] * ey[2];
+                const float ry1 = cf.r[3] * ey[0] + cf.r[4] * ey[1] + cf.r[5] * ey[2];
+                const float ry2 = cf.r[6] * ey[0] + cf.r[7] * ey[1] + cf.r[8] * ey[2];
+                // hx.X - uc*hx.Z = step*(fx*rx0 + (cx - uc)*rx2): the principal point cancels against uc
+                const float du = (float)(cv.cx - uc), dv = (float)(cv.cy - vc);
+                va.hxZ = step * rx2;
+                va.hyZ = step * ry2;
+                va.gxu = step * fmaf(du, rx2, cf.fx * rx0);
+                va.gyu = step * fmaf(du, ry2, cf.fx * ry0);
+                va.gxv = step * fmaf(dv, rx2, cf.fy * rx1);
+                va.gyv = step * fmaf(dv, ry2, cf.fy * ry1);
+                va.pad = 0.0f;
+                s_view[wib][slot] = va;
+                s_tex[wib][slot] = A.tex[v];
+            };
+
+            // sample view in slot `slot`: per-lane values (pivot-shifted) and the all-taps-inside flag
+            auto sample_view = [&](int slot, float (&d)[SPL], bool& usable) {
+                const float4* pv = reinterpret_cast<const float4*>(&s_view[wib][slot]);
+                const float4 q0 = pv[0], q1 = pv[1], q2 = pv[2];          // iu fu iv fv | Z0 hxZ hyZ gxu | gyu gxv gyv -
+                const cudaTextureObject_t tex = s_tex[wib][slot];
+                bool ok_all = true;
+                float val[SPL];
+#pragma unroll
+                for (int q = 0; q < SPL; ++q) {
+                    float u0, v0, fu, fv;
+                    bool front = true;
+                    if (reduce_a) {
+                        u0 = (float)col + aj[q];
+                        v0 = (float)row + ak[q];
+                        fu = fv = 0.0f;
+                    } else {
+                        const float z = fmaf(ak[q], q1.z, fmaf(aj[q], q1.y, q1.x));
+                        const float iz = 1.0f / z;
+                        const float tu = fmaf(fmaf(ak[q], q2.x, aj[q] * q1.w), iz, q0.y);
+                        const float tv = fmaf(fmaf(ak[q], q2.z, aj[q] * q2.y), iz, q0.w);
+                        const float flu = floorf(tu), flv = floorf(tv);
+                        u0 = q0.x + flu;
+                        v0 = q0.z + flv;
+                        fu = tu - flu;
+                        fv = tv - flv;
+                        front = z > 0.0f;
+                    }
+                    bool ok;
+                    val[q] = tap4(tex, u0, v0, fu, fv, front, A.W, A.H, ok);
+                    ok_all &= ok || !live[q];
+                }
+                usable = __all_sync(FULL, ok_all);
+                const float pivot = __shfl_sync(FULL, val[0], 0);
+#pragma unroll
+                for (int q = 0; q < SPL; ++q) d[q] = live[q] ? val[q] - pivot : 0.0f;
+            };
+
+            // ---- the reference view's own samples
+            float dref[SPL];
+            float Sr = 0.0f, SSr = 0.0f;
+            if (hyp_ok) {                                  // uniform across the warp
+                __syncwarp();
+                if (lane == 0) stage_view(r, 0);
+                __syncwarp();
+                bool usable;
+                sample_view(0, dref, usable);
+                hyp_ok = usable;
+                float s = 0.0f, ss = 0.0f;
+#pragma unroll
+                for (int q = 0; q < SPL; ++q) {
+                    s += dref[q];
+                    ss = fmaf(dref[q], dref[q], ss);
+                }
+                Sr = warp_sum(s);
+                SSr = warp_sum(ss);
+            }
+            const float ssr = SSr - Sr * Sr * (1.0f / NS);  // sum of squared deviations of the reference samples
+
+            double acc = 0.0;
+            int count = 0;
+            for (int w32 = 0; w32 < 2 * mw; ++w32) {       // 32 views per mask word
+                uint32_t word = 0u;
+                if (hyp_ok) {
+                    const uint32_t cand32 =
+                        A.cand ? (uint32_t)(__ldg(A.cand + h * mw + (w32 >> 1)) >> (32 * (w32 & 1))) : 0xffffffffu;
+#pragma unroll 1
+                    for (int half = 0; half < 2; ++half) {
+                        const int vbase = w32 * 32 + half * 16;
+                        if (vbase >= A.V) break;
+                        __syncwarp();
+                        if (lane < 16 && vbase + lane < A.V) stage_view(vbase + lane, lane);
+                        __syncwarp();
+                        float pa[16], pb[16], pc[16];
+                        uint32_t usable16 = 0u;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            pa[j] = pb[j] = pc[j] = 0.0f;
+                            if (vbase + j < A.V) {         // uniform
+                                float d[SPL];
+                                bool usable;
+                                sample_view(j, d, usable);
+                                if (usable) usable16 |= 1u << j;
+#pragma unroll
+                                for (int q = 0; q < SPL; ++q) {
+                                    pa[j] += d[q];
+                                    pb[j] = fmaf(d[q], d[q], pb[j]);
+                                    pc[j] = fmaf(d[q], dref[q], pc[j]);
+                                }
+                            }
+                        }
+                        const float Sd = butterfly16f(pa, lane);
+                        const float SSd = butterfly16f(pb, lane);
+                        const float SAB = butterfly16f(pc, lane);
+                        const int vj = lane_view16(lane);
+                        const int v = vbase + vj;
+                        const float ss = SSd - Sd * Sd * (1.0f / NS);
+                        const float cov = SAB - Sd * Sr * (1.0f / NS);
+                        const bool scored = (v < A.V) && (v != r) && ((usable16 >> vj) & 1u) &&
+                                            ((cand32 >> (half * 16 + vj)) & 1u) && (ss * (1.0f / NS) >= PMVS_VAR_MIN) &&
+                                            (ssr * (1.0f / NS) >= PMVS_VAR_MIN);
+                        const float val = cov * rsqrtf(ss * ssr) * cn;
+                        const bool vis = scored && (val > A.thr) && !(lane & 1);   // each view is held by a lane pair
+                        if (vis) acc += (double)val;
+                        word |= __reduce_or_sync(FULL, vis ? (1u << (half * 16 + vj)) : 0u);
+                        if (A.ncc_out && v < A.V && !(lane & 1)) A.ncc_out[h * A.V + v] = scored ? val : nanf("");
+                    }
+                } else if (A.ncc_out) {
+                    for (int v = w32 * 32 + lane; v < min(A.V, w32 * 32 + 32); v += 32) A.ncc_out[h * A.V + v] = nanf("");
+                }
+                count += __popc(word);
+                if (lane == 0 && A.vis_out) reinterpret_cast<uint32_t*>(A.vis_out)[h * 2 * mw + w32] = word;
+            }
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(FULL, acc, s);
+            const double avg = count > 0 ? acc / (double)count : 0.0;
+            if (lane == 0) {
+                if (A.count_out) A.count_out[h] = count;
+                if (A.avg_out) A.avg_out[h] = avg;
+            }
+            if (count >= A.bound && (float)avg > best_key) {   // strict '>': lowest index wins ties
+                best_key = (float)avg;
+                best_i = gi;
+            }
+        }
+        if (lane == 0 && A.best_idx) {
+            A.best_idx[set] = best_i;
+            if (A.best_avg) A.best_avg[set] = best_i >= 0 ? (double)best_key : 0.0;
+        }
+    }
+}
+
+// Argmax over consecutive hypothesis sets for already scored batches (either mode):
+// key = avg if count >= bound else -inf, lowest index on ties, -1 when none qualifies.
+__global__ void __launch_bounds__(256) select_best_sets(const double* __restrict__ avg, const int32_t* __restrict__ count,
+                                                        int64_t N, int group, int bound, int32_t* __restrict__ best_idx,
+                                                        double* __restrict__ best_avg) {
+    const int64_t n_sets = (N + group - 1) / group;
+    for (int64_t set = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; set < n_sets; set += (int64_t)gridDim.x * blockDim.x) {
+        double bk = -INFINITY;
+        int bi = -1;
+        for (int gi = 0; gi < group; ++gi) {
+            const int64_t h = set * group + gi;
+            if (h >= N) break;
+            if (count[h] >= bound && avg[h] > bk) {
+                bk = avg[h];
+                bi = gi;
+            }
+        }
+        best_idx[set] = bi;
+        if (best_avg) best_avg[set] = bi >= 0 ? bk : 0.0;
+    }
+}
+
+int mvs_launch_select_best(mvs_ctx* ctx, int64_t N, int group, const double* avg, const int32_t* count, int bound,
+                           int32_t* best_idx, double* best_avg, cudaStream_t s) {
+    if (N == 0) return MVS_OK;
+    const int64_t n_sets = (N + group - 1) / group;
+    int64_t blocks = (n_sets + 255) / 256;
+    const int64_t cap = (int64_t)ctx->sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    select_best_sets<<<(int)blocks, 256, 0, s>>>(avg, count, N, group, bound, best_idx, best_avg);
+    ctx->launches++;
+    MVS_CUDA_CHECK(cudaGetLastError());
+    return MVS_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// Texture path set-up (once per context, on the first Mode B call): one 2-D gather-enabled
+// CUDA array per view holding its gray image, a table of texture objects, fp32 cameras.
+// ---------------------------------------------------------------------------------
+int mvs_pmvs_prepare(mvs_ctx* ctx, cudaStream_t s) {
+    if (ctx->pmvs_ready) return MVS_OK;
+    const int V = ctx->V, H = ctx->H, W = ctx->W;
+    int rc = MVS_OK;
+    uint8_t* d_planar = nullptr;
+    CamProj* hp = nullptr;
+    CamProjF* hf = nullptr;
+    cudaTextureObject_t* htex = nullptr;
+    ctx->pmvs_arrays = (cudaArray_t*)calloc(V, sizeof(cudaArray_t));
+    ctx->pmvs_tex_host = (cudaTextureObject_t*)calloc(V, sizeof(cudaTextureObject_t));
+    hp = (CamProj*)malloc(sizeof(CamProj) * V);
+    hf = (CamProjF*)calloc(V, sizeof(CamProjF));
+    if (!ctx->pmvs_arrays || !ctx->pmvs_tex_host || !hp || !hf) { rc = MVS_ERR_NOMEM; goto done; }
+    htex = ctx->pmvs_tex_host;
+    if (cudaMalloc(&d_planar, (size_t)V * H * W) != cudaSuccess) {
+        cudaGetLastError();
+        mvs_set_error("Mode B set-up: cudaMalloc of %zu planar bytes failed", (size_t)V * H * W);
+        rc = MVS_ERR_NOMEM;
+        goto done;
+    }
+    if ((rc = mvs_launch_unpack_gray(ctx, d_planar, s)) != MVS_OK) goto done;
+    {
+        cudaChannelFormatDesc fmt = cudaCreateChannelDesc<unsigned char>();
+        for (int v = 0; v < V; ++v) {
+            if (cudaMallocArray(&ctx->pmvs_arrays[v], &fmt, W, H, cudaArrayTextureGather) != cudaSuccess) {
+                mvs_set_error("Mode B set-up: cudaMallocArray (%d x %d, view %d) failed: %s", W, H, v,
+                              cudaGetErrorString(cudaGetLastError()));
+                rc = MVS_ERR_NOMEM;
+                goto done;
+            }
+            if (cudaMemcpy2DToArrayAsync(ctx->pmvs_arrays[v], 0, 0, d_planar + (size_t)v * H * W, W, W, H,
+                                         cudaMemcpyDeviceToDevice, s) != cudaSuccess) {
+                mvs_set_error("Mode B set-up: copy to array failed: %s", cudaGetErrorString(cudaGetLastError()));
+                rc = MVS_ERR_CUDA;
+                goto done;
+            }
+            cudaResourceDesc rd;
+            memset(&rd, 0, sizeof(rd));
+            rd.resType = cudaResourceTypeArray;
+            rd.res.array.array = ctx->pmvs_arrays[v];
+            cudaTextureDesc td;
+            memset(&td, 0, sizeof(td));
+            td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+            td.filterMode = cudaFilterModePoint;
+            td.readMode = cudaReadModeNormalizedFloat;
+            td.normalizedCoords = 0;
+            if (cudaCreateTextureObject(&htex[v], &rd, &td, nullptr) != cudaSuccess) {
+                mvs_set_error("Mode B set-up: cudaCreateTextureObject failed: %s", cudaGetErrorString(cudaGetLastError()));
+                rc = MVS_ERR_CUDA;
+                goto done;
+            }
+        }
+    }
+    if (cudaMemcpy(hp, ctx->d_cam, sizeof(CamProj) * V, cudaMemcpyDeviceToHost) != cudaSuccess) { rc = MVS_ERR_CUDA; goto done; }
+    for (int v = 0; v < V; ++v) {
+        for (int i = 0; i < 9; ++i) hf[v].r[i] = (float)hp[v].r[i];
+        hf[v].fx = (float)hp[v].fx; hf[v].fy = (float)hp[v].fy; hf[v].cx = (float)hp[v].cx; hf[v].cy = (float)hp[v].cy;
+    }
+    if (cudaMalloc(&ctx->d_pmvs_tex, sizeof(cudaTextureObject_t) * V) != cudaSuccess ||
+        cudaMalloc(&ctx->d_pmvs_camf, sizeof(CamProjF) * V) != cudaSuccess) {
+        cudaGetLastError();
+        rc = MVS_ERR_NOMEM;
+        goto done;
+    }
+    if (cudaMemcpyAsync(ctx->d_pmvs_tex, htex, sizeof(cudaTextureObject_t) * V, cudaMemcpyHostToDevice, s) != cudaSuccess ||
+        cudaMemcpyAsync(ctx->d_pmvs_camf, hf, sizeof(CamProjF) * V, cudaMemcpyHostToDevice, s) != cudaSuccess ||
+        cudaStreamSynchronize(s) != cudaSuccess) {
+        mvs_set_error("Mode B set-up: upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+        rc = MVS_ERR_CUDA;
+        goto done;
+    }
+    ctx->pmvs_ready = 1;
+done:
+    if (d_planar) cudaFree(d_planar);
+    free(hp);
+    free(hf);
+    return rc;
+}
+
+void mvs_pmvs_release(mvs_ctx* ctx) {
+    if (ctx->pmvs_tex_host) {
+        for (int v = 0; v < ctx->V; ++v)
+            if (ctx->pmvs_tex_host[v]) cudaDestroyTextureObject(ctx->pmvs_tex_host[v]);
+        free(ctx->pmvs_tex_host);
+        ctx->pmvs_tex_host = nullptr;
+    }
+    if (ctx->pmvs_arrays) {
+        for (int v = 0; v < ctx->V; ++v)
+            if (ctx->pmvs_arrays[v]) cudaFreeArray(ctx->pmvs_arrays[v]);
+        free(ctx->pmvs_arrays);
+        ctx->pmvs_arrays = nullptr;
+    }
+    if (ctx->d_pmvs_tex) cudaFree(ctx->d_pmvs_tex);
+    if (ctx->d_pmvs_camf) cudaFree(ctx->d_pmvs_camf);
+    ctx->d_pmvs_tex = nullptr;
+    ctx->d_pmvs_camf = nullptr;
+    ctx->pmvs_ready = 0;
+}
+
+int mvs_launch_score_pmvs(mvs_ctx* ctx, int64_t N, const double* c, const double* nrm, const int32_t* ref,
+                          const uint64_t* cand, double thr, int mu, int flags, int group, int bound, uint64_t* vis,
+                          double* avg, int32_t* count, double* xy, float* ncc, int32_t* best_idx, double* best_avg,
+                          cudaStream_t s) {
+    if (N == 0) return MVS_OK;
+    int rc;
+    if ((rc = mvs_pmvs_prepare(ctx, s)) != MVS_OK) return rc;
+    PmvsArgs A;
+    A.cams = ctx->d_cam;
+    A.camsf = (const CamProjF*)ctx->d_pmvs_camf;
+    A.tex = (const cudaTextureObject_t*)ctx->d_pmvs_tex;
+    A.V = ctx->V; A.H = ctx->H; A.W = ctx->W;
+    A.flags = flags; A.group = group; A.bound = bound; A.thr = (float)thr;
+    A.c = c; A.nrm = nrm; A.ref = ref; A.cand = cand;
+    A.vis_out = vis; A.avg_out = avg; A.count_out = count; A.xy_out = xy; A.ncc_out = ncc;
+    A.best_idx = best_idx; A.best_avg = best_avg;
+    const int g = group > 1 ? group : 1;
+    const int64_t n_sets = (N + g - 1) / g;
+    int64_t blocks = (n_sets + 7) / 8;
+    const int64_t cap = (int64_t)ctx->sm_count * 2 * 4;
+    if (blocks > cap) blocks = cap;
+    const int pslot = (int)(ctx->prof_n % MVS_PROF_RING);
+    if (ctx->profile) MVS_CUDA_CHECK(cudaEventRecord(ctx->prof_ev[2 * pslot], s));
+    switch (mu) {
+        case 3: ncc_score_pmvs<3><<<(int)blocks, 256, 0, s>>>(A, N); break;
+        case 5: ncc_score_pmvs<5><<<(int)blocks, 256, 0, s>>>(A, N); break;
+        case 7: ncc_score_pmvs<7><<<(int)blocks, 256, 0, s>>>(A, N); break;
+        case 9: ncc_score_pmvs<9><<<(int)blocks, 256, 0, s>>>(A, N); break;
+        case 11: ncc_score_pmvs<11><<<(int)blocks, 256, 0, s>>>(A, N); break;
+        default: mvs_set_error("Mode B grid size mu = %d not supported (3, 5, 7, 9, 11)", mu); return MVS_ERR_ARG;
+    }
+    if (ctx->profile) {
+        MVS_CUDA_CHECK(cudaEventRecord(ctx->prof_ev[2 * pslot + 1], s));
+        ctx->prof_n++;
+    }
+    ctx->launches++;
+    MVS_CUDA_CHECK(cudaGetLastError());
+    return MVS_OK;
+}

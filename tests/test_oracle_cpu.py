@@ -110,3 +110,46 @@ def test_round_expansion_is_deterministic_and_fills_cells(golden):
     # sibling rule: a dj=+1 slot is never accepted together with its dj=-1 sibling
     acc = set(c1["slot"][c1["accepted"]].tolist())
     assert not any((s_ & 1) and (s_ - 1) in acc for s_ in acc)
+
+
+@pytest.mark.parametrize("mu,wid", [(11, 5), (5, 2), (7, 3)])
+def test_mode_b_spec_reduces_to_mode_a(golden, mu, wid):
+    """The Mode B specification (not in the reference) collapses onto the pinned Mode A oracle:
+    same camera for every view, integer lattice, no interpolation, Mode A bounds."""
+    from oracle import mode_a, mode_b
+    from oracle.cameras import Cameras
+    d = golden("dino12_scores")
+    cams = Cameras(d["K"], d["R"], d["t"])
+    gray = mode_a.gray_from_rgb(d["rgb"])
+    a = mode_a.score(gray, cams, d["c"], d["ref"], 0.7, wid=wid)
+    b = mode_b.score(gray, cams, d["c"], None, d["ref"], 0.7, mu=mu, reduce_to_mode_a=True)
+    assert np.array_equal(a["vis"], b["vis"])
+    assert np.array_equal(np.isnan(a["ncc"]), np.isnan(b["ncc"]))
+    assert np.nanmax(np.abs(a["ncc"] - b["ncc"])) < 1e-12
+    assert np.abs(a["avg"] - b["avg"]).max() < 1e-12
+    if wid == 5:
+        assert np.array_equal(b["vis"], d["t07_vis"])          # i.e. the reference's own output
+
+
+def test_mode_b_spec_prefers_true_surface():
+    """Self-consistency on a synthetic ring with known geometry: a patch on the true surface with
+    the true normal is seen by more views than a displaced or a tilted one."""
+    from mvs_b200 import rings
+    from oracle import mode_a, mode_b
+    from oracle.cameras import Cameras
+    rgb, K, R, t = rings.make_ring(12, 240, 320, seed=3)
+    cams = Cameras(K, R, t)
+    gray = mode_a.gray_from_rgb(rgb)
+    c, n, ref = rings.surface_hypotheses(600, K, R, t, seed=4)
+    cs = c / np.linalg.norm(c, axis=1, keepdims=True) * 0.045
+    ns = cs / 0.045
+    on = mode_b.score(gray, cams, cs, ns, ref, 0.7, mu=5)
+    off = mode_b.score(gray, cams, cs + ns * 0.004, ns, ref, 0.7, mu=5)
+    rng = np.random.default_rng(0)
+    tilt = mode_b.score(gray, cams, cs, ns + 0.8 * rng.normal(size=ns.shape), ref, 0.7, mu=5)
+    assert on["count"].mean() > 1.5 * off["count"].mean()
+    assert on["count"].mean() > tilt["count"].mean()
+    best, avg = mode_b.select_best(np.array([0.5, 0.9, 0.9, 0.2]), np.array([3, 3, 3, 1]), 3, 4)
+    assert best[0] == 1 and avg[0] == 0.9
+    best, _ = mode_b.select_best(np.array([0.5, 0.9]), np.array([1, 2]), 3, 2)
+    assert best[0] == -1
