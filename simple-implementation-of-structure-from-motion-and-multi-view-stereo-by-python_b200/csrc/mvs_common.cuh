@@ -66,6 +66,7 @@ struct mvs_ctx {
     int64_t prof_n;       // scoring kernels bracketed since mvs_profile_enable(1)
     // Mode B texture path (ncc_pmvs.cu), created on the first Mode B call
     int pmvs_ready;
+    int64_t pmvs_serial;
     cudaArray_t* pmvs_arrays;              // [V] host table of 2-D gather-enabled arrays
     cudaTextureObject_t* pmvs_tex_host;    // [V]
     void* d_pmvs_tex;                      // [V] cudaTextureObject_t

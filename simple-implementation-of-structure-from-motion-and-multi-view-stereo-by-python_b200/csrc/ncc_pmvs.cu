@@ -35,6 +35,12 @@ struct __align__(16) CamProjF {
     float pad[3];
 };
 
+// Texture handles of the views, read with a warp-uniform index: a handle that is provably
+// uniform lets TLD4 take it from a uniform register (no per-lane "waterfall" loop).  One table
+// per device; re-uploaded when another context scored last (mvs_launch_score_pmvs).
+#define PMVS_MAX_VIEWS 1024
+__constant__ cudaTextureObject_t c_tex[PMVS_MAX_VIEWS];
+
 struct PmvsArgs {
     const CamProj* cams;
     const CamProjF* camsf;
@@ -118,9 +124,9 @@ struct __align__(16) ViewAffine {
 // Bilinear sample through the gather path.  (u0, v0) = integer tap origin (pixel centres at
 // integers), (fu, fv) = fractions.  Returns the value in [0,1] and whether all four taps are
 // inside the image.
-__device__ __forceinline__ float tap4(cudaTextureObject_t tex, float u0, float v0, float fu, float fv, bool front, int W,
-                                      int H, bool& ok) {
-    ok = front && (u0 >= 0.0f) && (u0 <= (float)(W - 2)) && (v0 >= 0.0f) && (v0 <= (float)(H - 2));
+__device__ __forceinline__ float tap4(cudaTextureObject_t tex, float u0, float v0, float fu, float fv, bool front,
+                                      float wm2, float hm2, bool& ok) {
+    ok = front && (u0 >= 0.0f) && (u0 <= wm2) && (v0 >= 0.0f) && (v0 <= hm2);
     // the footprint of a gather at (u0+1, v0+1) is texels (u0..u0+1, v0..v0+1); the centre of
     // the 2x2 block is the robust coordinate.  Components: x=(0,1) y=(1,1) z=(1,0) w=(0,0) as
     // (column offset, row offset).
@@ -130,23 +136,27 @@ __device__ __forceinline__ float tap4(cudaTextureObject_t tex, float u0, float v
     return fmaf(fv, bot - top, top);
 }
 
-template <int MU>
-__global__ void __launch_bounds__(256, 2) ncc_score_pmvs(const PmvsArgs A, int64_t N) {
+template <int MU, bool REDUCE_A>
+__global__ void __launch_bounds__(32, 16) ncc_score_pmvs(const PmvsArgs A, int64_t N) {
     constexpr int NS = MU * MU;
     constexpr int SPL = (NS + 31) / 32;                    // samples per lane
     constexpr float HALF = 0.5f * (MU - 1);
-    __shared__ ViewAffine s_view[8][16];
-    __shared__ cudaTextureObject_t s_tex[8][16];
+    // ONE WARP PER CTA: every loop bound and view index below then derives from blockIdx and the
+    // kernel arguments only, i.e. is provably warp-uniform, which lets the texture handle travel
+    // in a uniform register (no per-lane waterfall loop around TLD4) and keeps the gathers of a
+    // batch of views in flight together.
+    __shared__ ViewAffine s_view[1][33];                   // 32 views of the current block + the reference view
 
-    const int lane = threadIdx.x & 31;
-    const int wib = threadIdx.x >> 5;
-    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x;
+    constexpr int wib = 0;
+    const int64_t warp0 = blockIdx.x;
+    const int64_t nwarps = gridDim.x;
     const int mw = (A.V + 63) >> 6;
     const int group = A.group > 1 ? A.group : 1;
     const int64_t n_sets = (N + group - 1) / group;
     const float cn = (float)NS / (float)(NS - 1);
-    const bool reduce_a = (A.flags & MVS_PMVS_REDUCE_TO_REFEXACT) != 0;
+    constexpr bool reduce_a = REDUCE_A;
+    const float wm2 = (float)(A.W - 2), hm2 = (float)(A.H - 2);
 
     // this lane's sample offsets on the grid (m = k*MU + j)
     float aj[SPL], ak[SPL];
@@ -235,16 +245,14 @@ __global__ void __launch_bounds__(256, 2) ncc_score_pmvs(const PmvsArgs A, int64
                 va.gyv = step * fmaf(dv, ry2, cf.fy * ry1);
                 va.pad = 0.0f;
                 s_view[wib][slot] = va;
-                s_tex[wib][slot] = A.tex[v];
             };
 
-            // sample view in slot `slot`: per-lane values (pivot-shifted) and the all-taps-inside flag
-            auto sample_view = [&](int slot, float (&d)[SPL], bool& usable) {
+            // Issue the taps of the view staged in `slot` (no warp-synchronous operation in here,
+            // so the gathers of a whole batch of views are in flight together).
+            auto issue_view = [&](int slot, cudaTextureObject_t tex, float (&val)[SPL], bool& ok_all) {
                 const float4* pv = reinterpret_cast<const float4*>(&s_view[wib][slot]);
                 const float4 q0 = pv[0], q1 = pv[1], q2 = pv[2];          // iu fu iv fv | Z0 hxZ hyZ gxu | gyu gxv gyv -
-                const cudaTextureObject_t tex = s_tex[wib][slot];
-                bool ok_all = true;
-                float val[SPL];
+                ok_all = true;
 #pragma unroll
                 for (int q = 0; q < SPL; ++q) {
                     float u0, v0, fu, fv;
@@ -255,7 +263,7 @@ __global__ void __launch_bounds__(256, 2) ncc_score_pmvs(const PmvsArgs A, int64
                         fu = fv = 0.0f;
                     } else {
                         const float z = fmaf(ak[q], q1.z, fmaf(aj[q], q1.y, q1.x));
-                        const float iz = 1.0f / z;
+                        const float iz = __fdividef(1.0f, z);
                         const float tu = fmaf(fmaf(ak[q], q2.x, aj[q] * q1.w), iz, q0.y);
                         const float tv = fmaf(fmaf(ak[q], q2.z, aj[q] * q2.y), iz, q0.w);
                         const float flu = floorf(tu), flv = floorf(tv);
@@ -266,40 +274,41 @@ __global__ void __launch_bounds__(256, 2) ncc_score_pmvs(const PmvsArgs A, int64
                         front = z > 0.0f;
                     }
                     bool ok;
-                    val[q] = tap4(tex, u0, v0, fu, fv, front, A.W, A.H, ok);
+                    val[q] = tap4(tex, u0, v0, fu, fv, front, wm2, hm2, ok);
                     ok_all &= ok || !live[q];
                 }
-                usable = __all_sync(FULL, ok_all);
-                const float pivot = __shfl_sync(FULL, val[0], 0);
-#pragma unroll
-                for (int q = 0; q < SPL; ++q) d[q] = live[q] ? val[q] - pivot : 0.0f;
             };
-
-            // ---- the reference view's own samples
-            float dref[SPL];
-            float Sr = 0.0f, SSr = 0.0f;
-            if (hyp_ok) {                                  // uniform across the warp
-                __syncwarp();
-                if (lane == 0) stage_view(r, 0);
-                __syncwarp();
-                bool usable;
-                sample_view(0, dref, usable);
-                hyp_ok = usable;
-                float s = 0.0f, ss = 0.0f;
-#pragma unroll
-                for (int q = 0; q < SPL; ++q) {
-                    s += dref[q];
-                    ss = fmaf(dref[q], dref[q], ss);
-                }
-                Sr = warp_sum(s);
-                SSr = warp_sum(ss);
-            }
-            const float ssr = SSr - Sr * Sr * (1.0f / NS);  // sum of squared deviations of the reference samples
 
             double acc = 0.0;
             int count = 0;
+            float dref[SPL];
+            float Sr = 0.0f, ssr = 0.0f;
             for (int w32 = 0; w32 < 2 * mw; ++w32) {       // 32 views per mask word
                 uint32_t word = 0u;
+                if (hyp_ok) {                              // uniform across the warp
+                    // ---- stage this block's 32 views (one lane each); block 0 also stages the reference view
+                    __syncwarp();
+                    stage_view(min(w32 * 32 + lane, A.V - 1), lane);       // lanes past the last view shadow it
+                    if (w32 == 0 && r >= 32 && lane == 0) stage_view(r, 32);
+                    __syncwarp();
+                    if (w32 == 0) {
+                        // ---- the reference view's own samples
+                        bool ok_all;
+                        float val[SPL];
+                        issue_view(r < 32 ? r : 32, A.tex[r], val, ok_all);
+                        hyp_ok = __all_sync(FULL, ok_all);
+                        const float pivot = __shfl_sync(FULL, val[0], 0);
+                        float s = 0.0f, ss = 0.0f;
+#pragma unroll
+                        for (int q = 0; q < SPL; ++q) {
+                            dref[q] = live[q] ? val[q] - pivot : 0.0f;
+                            s += dref[q];
+                            ss = fmaf(dref[q], dref[q], ss);
+                        }
+                        Sr = warp_sum(s);
+                        ssr = warp_sum(ss) - Sr * Sr * (1.0f / NS);  // sum of squared deviations of the reference samples
+                    }
+                }
                 if (hyp_ok) {
                     const uint32_t cand32 =
                         A.cand ? (uint32_t)(__ldg(A.cand + h * mw + (w32 >> 1)) >> (32 * (w32 & 1))) : 0xffffffffu;
@@ -307,24 +316,30 @@ __global__ void __launch_bounds__(256, 2) ncc_score_pmvs(const PmvsArgs A, int64
                     for (int half = 0; half < 2; ++half) {
                         const int vbase = w32 * 32 + half * 16;
                         if (vbase >= A.V) break;
-                        __syncwarp();
-                        if (lane < 16 && vbase + lane < A.V) stage_view(vbase + lane, lane);
-                        __syncwarp();
                         float pa[16], pb[16], pc[16];
                         uint32_t usable16 = 0u;
+                        constexpr int TB = SPL == 1 ? 16 : (SPL == 2 ? 8 : 4);   // views whose gathers fly together
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            pa[j] = pb[j] = pc[j] = 0.0f;
-                            if (vbase + j < A.V) {         // uniform
-                                float d[SPL];
-                                bool usable;
-                                sample_view(j, d, usable);
-                                if (usable) usable16 |= 1u << j;
+                        for (int j0 = 0; j0 < 16; j0 += TB) {
+                            float val[TB][SPL];
+                            bool okl[TB];
+#pragma unroll
+                            for (int jj = 0; jj < TB; ++jj) {
+                                // views past the last one re-sample it (branch-free); their sums are never scored
+                                issue_view(half * 16 + j0 + jj, c_tex[min(vbase + j0 + jj, A.V - 1)], val[jj], okl[jj]);
+                            }
+#pragma unroll
+                            for (int jj = 0; jj < TB; ++jj) {
+                                const int j = j0 + jj;
+                                if (__all_sync(FULL, okl[jj])) usable16 |= 1u << j;
+                                const float pivot = __shfl_sync(FULL, val[jj][0], 0);
+                                pa[j] = pb[j] = pc[j] = 0.0f;
 #pragma unroll
                                 for (int q = 0; q < SPL; ++q) {
-                                    pa[j] += d[q];
-                                    pb[j] = fmaf(d[q], d[q], pb[j]);
-                                    pc[j] = fmaf(d[q], dref[q], pc[j]);
+                                    const float d = live[q] ? val[jj][q] - pivot : 0.0f;
+                                    pa[j] += d;
+                                    pb[j] = fmaf(d, d, pb[j]);
+                                    pc[j] = fmaf(d, dref[q], pc[j]);
                                 }
                             }
                         }
@@ -480,6 +495,10 @@ int mvs_pmvs_prepare(mvs_ctx* ctx, cudaStream_t s) {
         goto done;
     }
     ctx->pmvs_ready = 1;
+    {
+        static int64_t serial = 0;                 // distinguishes a new context allocated at a recycled address
+        ctx->pmvs_serial = ++serial;
+    }
 done:
     if (d_planar) cudaFree(d_planar);
     free(hp);
@@ -514,6 +533,15 @@ int mvs_launch_score_pmvs(mvs_ctx* ctx, int64_t N, const double* c, const double
     if (N == 0) return MVS_OK;
     int rc;
     if ((rc = mvs_pmvs_prepare(ctx, s)) != MVS_OK) return rc;
+    // the constant-memory handle table belongs to the context that scored last on this device
+    static const mvs_ctx* table_owner[64] = {nullptr};
+    static int64_t table_serial[64] = {0};
+    if (ctx->device < 64 && (table_owner[ctx->device] != ctx || table_serial[ctx->device] != ctx->pmvs_serial)) {
+        MVS_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_tex, ctx->pmvs_tex_host, sizeof(cudaTextureObject_t) * ctx->V, 0,
+                                               cudaMemcpyHostToDevice, s));
+        table_owner[ctx->device] = ctx;
+        table_serial[ctx->device] = ctx->pmvs_serial;
+    }
     PmvsArgs A;
     A.cams = ctx->d_cam;
     A.camsf = (const CamProjF*)ctx->d_pmvs_camf;
@@ -525,19 +553,23 @@ int mvs_launch_score_pmvs(mvs_ctx* ctx, int64_t N, const double* c, const double
     A.best_idx = best_idx; A.best_avg = best_avg;
     const int g = group > 1 ? group : 1;
     const int64_t n_sets = (N + g - 1) / g;
-    int64_t blocks = (n_sets + 7) / 8;
-    const int64_t cap = (int64_t)ctx->sm_count * 2 * 4;
+    int64_t blocks = n_sets;                               // one warp per CTA
+    const int64_t cap = (int64_t)ctx->sm_count * 16 * 4;
     if (blocks > cap) blocks = cap;
     const int pslot = (int)(ctx->prof_n % MVS_PROF_RING);
     if (ctx->profile) MVS_CUDA_CHECK(cudaEventRecord(ctx->prof_ev[2 * pslot], s));
+#define PMVS_LAUNCH(MU_)                                                     \
+    case MU_:                                                                \
+        if (flags & MVS_PMVS_REDUCE_TO_REFEXACT)                             \
+            ncc_score_pmvs<MU_, true><<<(int)blocks, 32, 0, s>>>(A, N);      \
+        else                                                                 \
+            ncc_score_pmvs<MU_, false><<<(int)blocks, 32, 0, s>>>(A, N);     \
+        break;
     switch (mu) {
-        case 3: ncc_score_pmvs<3><<<(int)blocks, 256, 0, s>>>(A, N); break;
-        case 5: ncc_score_pmvs<5><<<(int)blocks, 256, 0, s>>>(A, N); break;
-        case 7: ncc_score_pmvs<7><<<(int)blocks, 256, 0, s>>>(A, N); break;
-        case 9: ncc_score_pmvs<9><<<(int)blocks, 256, 0, s>>>(A, N); break;
-        case 11: ncc_score_pmvs<11><<<(int)blocks, 256, 0, s>>>(A, N); break;
+        PMVS_LAUNCH(3) PMVS_LAUNCH(5) PMVS_LAUNCH(7) PMVS_LAUNCH(9) PMVS_LAUNCH(11)
         default: mvs_set_error("Mode B grid size mu = %d not supported (3, 5, 7, 9, 11)", mu); return MVS_ERR_ARG;
     }
+#undef PMVS_LAUNCH
     if (ctx->profile) {
         MVS_CUDA_CHECK(cudaEventRecord(ctx->prof_ev[2 * pslot + 1], s));
         ctx->prof_n++;

@@ -101,3 +101,58 @@ def surface_hypotheses(N, K, R, t, obj_r=0.045, seed=2, jitter=0.002):
     n = C[ref] - c
     n /= np.linalg.norm(n, axis=1, keepdims=True)
     return c, n, ref
+
+
+def make_ring_device(V, H=480, W=640, obj_r=0.045, seed=1, elev=0.35, device="cuda"):
+    """The same ring rendered with torch on ``device`` (for the large rings: 128 x 1080p,
+    256 x 4K take minutes in NumPy).  Input synthesis only -- returns a [V,H,W,3] uint8 CUDA
+    tensor plus K, R, t (NumPy).  Not bit-identical to ``make_ring`` (fp32 sin on another unit)."""
+    import torch
+    K, R, t = ring_cameras(V, H, W, elev=elev)
+    rng = np.random.default_rng(seed)
+    waves = []
+    for ch in range(3):
+        for k in range(6):
+            d = rng.normal(size=3)
+            d /= np.linalg.norm(d)
+            waves.append((ch, k, d.astype(np.float32), np.float32(rng.uniform(400.0, 2600.0)), np.float32(rng.uniform(0, 2 * np.pi))))
+    out = torch.empty((V, H, W, 3), dtype=torch.uint8, device=device)
+    for v in range(V):
+        fx, fy, cx, cy = K[v][0, 0], K[v][1, 1], K[v][0, 2], K[v][1, 2]
+        Rv = torch.tensor(R[v], dtype=torch.float32, device=device)
+        Cf = torch.tensor(-R[v].T @ t[v], dtype=torch.float32, device=device)
+        u = (torch.arange(W, dtype=torch.float32, device=device) + 0.5 - float(cx)) / float(fx)
+        w = (torch.arange(H, dtype=torch.float32, device=device) + 0.5 - float(cy)) / float(fy)
+        vv, uu = torch.meshgrid(w, u, indexing="ij")
+        d = torch.stack([uu, vv, torch.ones_like(uu)], -1) @ Rv
+        d = d / d.norm(dim=-1, keepdim=True)
+        b = d @ Cf
+        disc = b * b - (Cf @ Cf - obj_r * obj_r)
+        hit = disc > 0
+        tt = -b - torch.sqrt(torch.where(hit, disc, torch.zeros_like(disc)))
+        P = Cf + tt[..., None] * d
+        shade = (0.35 + 0.65 * ((P / obj_r) * (-d)).sum(-1).abs()).clamp(0, 1)
+        img = torch.zeros((H, W, 3), dtype=torch.float32, device=device)
+        for ch, k, dk, freq, ph in waves:
+            img[..., ch] += torch.sin((P @ torch.tensor(dk, device=device)) * float(freq) + float(ph)) / (1 + 0.3 * k)
+        img = (128.0 + 40.0 * img).clamp(1, 255) * shade[..., None]
+        out[v] = torch.where(hit[..., None], img, torch.zeros_like(img)).to(torch.uint8)
+    return out, K, R, t
+
+
+def hypothesis_sets(n_cells, K, R, t, depths=8, normals=8, obj_r=0.045, seed=2, depth_span=0.004, tilt=0.35):
+    """BASELINE.json config 3: ``n_cells`` surface cells x ``depths`` depth offsets x ``normals``
+    normal tilts = one selection set of depths*normals hypotheses per cell, consecutive in memory.
+    Returns c, n [N,3], ref [N] with N = n_cells*depths*normals."""
+    rng = np.random.default_rng(seed)
+    c0, n0, ref0 = surface_hypotheses(n_cells, K, R, t, obj_r=obj_r, seed=seed, jitter=0.0)
+    G = depths * normals
+    dd = np.linspace(-depth_span, depth_span, depths)
+    ray = n0                                                  # towards the reference camera
+    c = np.repeat(c0, G, axis=0) + np.repeat(ray, G, axis=0) * np.tile(np.repeat(dd, normals), n_cells)[:, None]
+    true_n = c0 / np.linalg.norm(c0, axis=1, keepdims=True)
+    tl = rng.normal(size=(n_cells * G, 3)) * tilt
+    tl.reshape(n_cells, G, 3)[:, ::normals] = 0.0             # first normal of each depth: the true one
+    n = np.repeat(true_n, G, axis=0) + tl
+    n /= np.linalg.norm(n, axis=1, keepdims=True)
+    return c, n, np.repeat(ref0, G).astype(np.int32)
