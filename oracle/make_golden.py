@@ -328,8 +328,34 @@ def make_full(ref_mvs2, imgs, par_text, n=1024):
                         Rrt=cv_roundtrip(R), c=c, ref=ref, thresholds=np.array([0.4, 0.7]), **out)
 
 
+def make_tracks():
+    """Runs the reference's own sparse stage (SFM.StructureFromMotion, SFM.py:47, unmodified) on
+    dinoRing and records what MVS consumes from it: the 2-D observation tracks of
+    global_set.getInfo() (GlobalSet.py:36-50).  SfM is not deterministic run to run (FLANN's
+    randomised kd-trees, utils.py:180-185): this is ONE instance, committed so that the dense
+    stage can be run and measured on the GPU box where the reference does not exist."""
+    ref_mvs2, ref_main = import_reference()
+    import GlobalSet as ref_gs
+    import SFM as ref_sfm
+    args = types.SimpleNamespace(img_dir=os.path.join(REF, "dinoRing") + "/", par_path=os.path.join(REF, "dinoRing", "dinoR_par.txt"),
+                                 img_type="png", scale=10.0, debug=False, nonSeq=False, cell_size=2, desc_wid=5)
+    with contextlib.redirect_stdout(io.StringIO()):
+        imgs = ref_main.read_imgs(args)
+        gs = ref_gs.GlobalSet(threshold=0.01)
+        ref_sfm.StructureFromMotion(imgs, gs, args, 0.3)
+        n_obs, n_pts, legal_sets = gs.getInfo()
+    obs, offs = [], [0]
+    for ls in legal_sets:
+        for cam, x, y in ls.point2d_list:
+            obs.append((float(cam), float(x), float(y)))
+        offs.append(len(obs))
+    np.savez_compressed(os.path.join(GOLD, "dino_tracks.npz"), obs=np.array(obs), offsets=np.array(offs, dtype=np.int64))
+    return len(offs) - 1, len(obs)
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--tracks", action="store_true", help="only (re)record the SfM tracks of dinoRing")
     ap.add_argument("--full", action="store_true")
     ap.add_argument("--full-n", type=int, default=1024)
     ap.add_argument("--only-full", action="store_true", help="leave the committed fixtures untouched")
@@ -337,6 +363,9 @@ def main():
     if not os.path.isdir(REF):
         raise SystemExit("reference not mounted at /root/reference: golden vectors can only be made in the build container")
     os.makedirs(GOLD, exist_ok=True)
+    if a.tracks:
+        print("dino_tracks: %d tracks, %d observations" % make_tracks())
+        return
     ref_mvs2, ref_main = import_reference()
     imgs, par_text = load_dino(ref_main)
     if a.only_full:

@@ -1,0 +1,102 @@
+"""BASELINE.json config 2: the full dense stage on dinoRing (48 views 640x480, -scale 10, cell size 2)
+through the MVS2 drop-in, restructured into synchronous rounds, on the GPUs of one box.
+
+Inputs (the reference itself cannot travel to the GPU box): the image stack + cameras recorded by
+oracle/make_golden.py --only-full (oracle/_ref/dinoRing_full.npz, git-ignored, shipped with the repo
+snapshot) and ONE instance of the reference's own SfM tracks (tests/golden/dino_tracks.npz, made
+by oracle/make_golden.py --tracks).  Writes a JSON summary: rounds, candidates per round, ms per
+round (CUDA events), scored hypotheses/s, final patch count.
+
+    python profiles/run_dino_rounds.py [--max-rounds N] [--out gpurun_out/dino_rounds.json]
+"""
+import argparse
+import json
+import os
+import sys
+import tempfile
+import time
+import types
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+class _Track:
+    def __init__(self, pts):
+        self.point2d_list = pts
+
+
+class _GlobalSet:
+    """What MVS reads from SfM: GlobalSet.getInfo() (GlobalSet.py:36-50)."""
+
+    def __init__(self, obs, offsets):
+        self.sets = [_Track([(int(obs[k, 0]), float(obs[k, 1]), float(obs[k, 2])) for k in range(offsets[i], offsets[i + 1])])
+                     for i in range(len(offsets) - 1)]
+        self.n_obs = len(obs)
+
+    def getInfo(self):
+        return self.n_obs, len(self.sets), self.sets
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--max-rounds", type=int, default=100000)
+    ap.add_argument("--max-iterations", type=int, default=100000)  # the reference's iteration cap, MVS2.py:321
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "dino_rounds.json"))
+    a = ap.parse_args()
+    full = os.path.join(ROOT, "oracle", "_ref", "dinoRing_full.npz")
+    if not os.path.exists(full):
+        raise SystemExit(full + " is missing: run `python -m oracle.make_golden --only-full` in the build container")
+    d = np.load(full)
+    tr = np.load(os.path.join(ROOT, "tests", "golden", "dino_tracks.npz"))
+    V = d["rgb"].shape[0]
+    work = tempfile.mkdtemp(prefix="dino_rounds_")
+    par = os.path.join(work, "dinoR_par.txt")
+    with open(par, "w") as f:                                       # utils.py:56-81 layout
+        f.write("%d\n" % V)
+        for v in range(V):
+            vals = list(d["K"][v].ravel()) + list(d["R"][v].ravel()) + list(d["t"][v].ravel())
+            f.write("dinoR%04d.png " % (v + 1) + " ".join(repr(float(x)) for x in vals) + "\n")
+    os.environ["MVS_MAX_ROUNDS"] = str(a.max_rounds)
+    os.environ["MVS_MAX_ITERATIONS"] = str(a.max_iterations)
+    os.environ["MVS_TIME_ROUNDS"] = "1"
+    from mvs_b200 import MVS2
+    args = types.SimpleNamespace(par_path=par, scale=10.0, cell_size=2, desc_wid=5, debug=False)
+    imgs = [d["rgb"][v] for v in range(V)]
+    gs = _GlobalSet(tr["obs"], tr["offsets"])
+    cwd = os.getcwd()
+    os.chdir(work)
+    t0 = time.time()
+    try:
+        MVS2.DensePointsWithMVS2(imgs, gs, args)
+    finally:
+        os.chdir(cwd)
+    wall = time.time() - t0
+    stats = MVS2.patch_expansion.last_stats
+    ms = [s.get("ms", 0.0) for s in stats]
+    cands = [s["candidates"] for s in stats]
+    acc = [s["accepted"] for s in stats]
+    ply = os.path.join(work, "all_patches.ply")
+    n_all = os.path.getsize(ply) if os.path.exists(ply) else None
+    out = {
+        "config": "dinoRing 48 views 640x480, -scale 10, cell_size 2, MIN_NCC 0.4 (seeds) / 0.7 (expansion), patches expanded capped at the reference's 100000 iterations (MVS2.py:321)",
+        "tracks": len(gs.sets), "rounds": len(stats), "candidates_scored": int(sum(cands)), "patches_accepted": int(sum(acc)),
+        "expansion_device_ms": float(sum(ms)), "ms_per_round_mean": float(np.mean(ms)) if ms else None,
+        "ms_per_round_median": float(np.median(ms)) if ms else None,
+        "candidates_per_round_mean": float(np.mean(cands)) if cands else None, "candidates_per_round_max": int(max(cands)) if cands else None,
+        "hypotheses_per_s_device": float(sum(cands) / (sum(ms) * 1e-3)) if sum(ms) > 0 else None,
+        "dense_stage_wall_s": wall, "all_patches_ply_bytes": n_all, "iterations_cap": a.max_iterations,
+        "rounds_detail": stats[:64],
+        "note": "ms per round = CUDA events around generate + score + (all-gather) + commit, including the host "
+                "syncs the round protocol needs; reference for scale: 300 sequential iterations = 10 418 scorer calls "
+                "took 224 s on the CPU (SURVEY.md section 6)",
+    }
+    os.makedirs(os.path.dirname(a.out), exist_ok=True)
+    json.dump(out, open(a.out, "w"), indent=1)
+    print(json.dumps({k: v for k, v in out.items() if k != "rounds_detail"}))
+
+
+if __name__ == "__main__":
+    main()

@@ -276,11 +276,13 @@ def patch_expansion(args, imgs, initial_patches, cells, camera_pos, visible_lowe
             rank, world = dist.get_rank(), dist.get_world_size()
     except ImportError:
         pass
-    drv = RoundDriver(be, rank=rank, world=world, group=group)
-    max_rounds = int(os.environ.get("MVS_MAX_ROUNDS", "100000"))          # the reference caps iterations at 100000
+    drv = RoundDriver(be, rank=rank, world=world, group=group, timing=bool(os.environ.get("MVS_TIME_ROUNDS")))
+    max_rounds = int(os.environ.get("MVS_MAX_ROUNDS", "100000"))
+    max_iter = int(os.environ.get("MVS_MAX_ITERATIONS", "100000"))        # the reference's cap: iteration < 100000 (MVS2.py:321)
     max_patches = os.environ.get("MVS_MAX_PATCHES")
     accepted = drv.run(be.to_device(_patches_to_records(initial_patches, V)), max_rounds=max_rounds,
-                       max_patches=int(max_patches) if max_patches else None)
+                       max_patches=int(max_patches) if max_patches else None, max_iterations=max_iter)
+    drv.finish_timing()
     new_tab = be.table()
     for v in range(V):
         cells.table[v][...] = new_tab[v]

@@ -99,10 +99,12 @@ class RoundDriver:
     """Runs rounds over a backend; with ``world > 1`` candidates are sharded by index and the
     accepted records all-gathered (torch.distributed: NCCL on GPUs, gloo in CPU tests)."""
 
-    def __init__(self, backend, rank=0, world=1, group=None):
+    def __init__(self, backend, rank=0, world=1, group=None, timing=False):
         self.b = backend
         self.rank, self.world, self.group = rank, world, group
         self.stats = []
+        self.timing = timing and hasattr(backend, "torch")       # CUDA events around every round
+        self._events = []
 
     def _gather(self, recs, n_local):
         import torch
@@ -121,6 +123,24 @@ class RoundDriver:
         return torch.cat([out[r, :counts_h[r]] for r in range(self.world)]), counts_h
 
     def round(self, frontier):
+        if self.timing:
+            ev = (self.b.torch.cuda.Event(enable_timing=True), self.b.torch.cuda.Event(enable_timing=True))
+            ev[0].record()
+            nxt = self._round(frontier)
+            ev[1].record()
+            self._events.append(ev)
+            return nxt
+        return self._round(frontier)
+
+    def finish_timing(self):
+        """ms per round (device time between the round's first and last enqueued work)."""
+        if self.timing and self._events:
+            self.b.torch.cuda.synchronize()
+            for st, (a, b) in zip(self.stats, self._events):
+                st["ms"] = a.elapsed_time(b)
+        return self.stats
+
+    def _round(self, frontier):
         M = self.b.generate(frontier)
         begin, end = shard_bounds(M, self.rank, self.world)
         recs, n_local = self.b.score(frontier, begin, end)
@@ -134,15 +154,24 @@ class RoundDriver:
                                accepted=int(nxt.shape[0])))
         return nxt
 
-    def run(self, seeds, max_rounds=1000, max_patches=None):
+    def run(self, seeds, max_rounds=1000, max_patches=None, max_iterations=None):
         """seeds: device record tensor (already filled into the table by the caller).  Returns
-        the list of per-round accepted record tensors."""
+        the list of per-round accepted record tensors.  ``max_iterations`` caps the number of
+        patches EXPANDED, like the reference's ``iteration < 100000`` (MVS2.py:321: one iteration =
+        one patch popped from the queue); the last frontier is cut to the remaining budget in slot
+        order, so the cap is independent of the GPU count."""
         frontier = seeds
         accepted = []
         total = 0
+        expanded = 0
         for _ in range(max_rounds):
             if frontier.shape[0] == 0:
                 break
+            if max_iterations is not None:
+                if expanded >= max_iterations:
+                    break
+                frontier = frontier[: max_iterations - expanded]
+            expanded += frontier.shape[0]
             frontier = self.round(frontier)
             if frontier.shape[0]:
                 accepted.append(frontier)
