@@ -345,7 +345,13 @@ extern "C" int mvs_score_batch(mvs_ctx* ctx, int mode, int64_t N, const double* 
     // host mode: a three-stage pipeline over chunks of the batch -- H2D of chunk k+1, the kernels of
     // chunk k and D2H of chunk k-1 run concurrently on three streams (PCIe is full duplex), three
     // staging slots.  Synchronises before returning.
-    const int64_t CH = N > (1 << 18) ? (1 << 17) : N;       // hypotheses per chunk
+    static int64_t chunk_pref = 0;                          // MVS_HOST_CHUNK: tuning knob (hypotheses per chunk)
+    if (chunk_pref == 0) {
+        const char* e = getenv("MVS_HOST_CHUNK");
+        chunk_pref = e ? atoll(e) : (1 << 18);
+        if (chunk_pref < 1024) chunk_pref = 1 << 18;
+    }
+    const int64_t CH = N > 2 * chunk_pref ? chunk_pref : N;  // hypotheses per chunk
     const size_t b_c = align256(sizeof(double) * 3 * CH), b_ref = align256(sizeof(int32_t) * CH);
     const size_t b_vis = align256(sizeof(uint64_t) * mw * CH), b_avg = align256(sizeof(double) * CH);
     const size_t b_cnt = align256(sizeof(int32_t) * CH), b_xy = align256(sizeof(double) * 2 * CH);
