@@ -308,6 +308,35 @@ def run_b200(args):
     sp = C.c_void_p(stream.cuda_stream)
     p = lambda x: C.c_void_p(x.data_ptr())
 
+    # N > 1, Mode A: the round's batch can be scored in NCH chunks with the all-gather of chunk i (counts,
+    # then payload, on a second stream) overlapping the scoring of chunk i+1 (BENCH_EXCHANGE_CHUNKS).
+    # Measured at N = 2: 4 chunks are SLOWER (1.31 vs 0.88 ms/step: quarter-size K1 launches lose their
+    # L1 reuse and share the SMs with the NCCL kernels), so the default is one chunk = one all-gather per round.
+    NCH = int(os.environ.get("BENCH_EXCHANGE_CHUNKS", "1")) if (world > 1 and not mode_b) else 1
+    bounds = [(n * i // NCH, n * (i + 1) // NCH) for i in range(NCH)]
+    comm = torch.cuda.Stream(device=dev) if world > 1 else None
+    n_acc_ch = torch.zeros(NCH, dtype=torch.int64, device=dev)
+    counts_ch = torch.zeros((NCH, world), dtype=torch.int64, device=dev)
+    counts_host = torch.zeros((NCH, world), dtype=torch.int64).pin_memory()
+    outs = None
+
+    def make_outs():
+        mw_ = (V + 63) // 64
+        full = dict(vis_mask=torch.empty((n, mw_), dtype=torch.int64, device=dev), avg=torch.empty(n, dtype=torch.float64, device=dev),
+                    count=torch.empty(n, dtype=torch.int32, device=dev), xy=torch.empty((n, 2), dtype=torch.float64, device=dev))
+        return full, [{k: v[lo:hi] for k, v in full.items()} for lo, hi in bounds]
+
+    if not mode_b:
+        out, outs = make_outs()
+
+    def gather_payload(ch, ev_counts):
+        lo, hi = bounds[ch]
+        ev_counts.synchronize()                               # host: this chunk's counts (later chunks are already enqueued)
+        mx = max(int(counts_host[ch].max()), 1)
+        with torch.cuda.stream(comm):
+            dst = gbuf[world * lo * rec_bytes: world * lo * rec_bytes + world * mx * rec_bytes].view(world * mx, rec_bytes)
+            dist.all_gather_into_tensor(dst, records[lo:lo + mx])
+
     def step():
         if mode_b:
             ctx.score_pmvs_device(d_c, d_n, d_ref, min_ncc=THR, mu=w["mu"], group=group, bound=BOUND, out=out,
@@ -316,16 +345,30 @@ def run_b200(args):
                 dist.all_gather_into_tensor(g_idx, out["best_idx"])
                 dist.all_gather_into_tensor(g_avg, out["best_avg"])
             return
-        ctx.score_device(d_c, d_ref, min_ncc=THR, wid=w["wid"], out=out, stream=stream.cuda_stream)
-        rc = lib.mvs_compact_accepted(ctx._h, n, rank * n, p(d_c), p(d_n), p(d_ref), p(out["vis_mask"]), p(out["avg"]),
-                                      p(out["count"]), p(out["xy"]), None, BOUND, p(records), n, p(n_acc), sp)
-        if rc != 0:
-            raise RuntimeError(lib.mvs_last_error().decode())
+        pending = None
+        for ch, (lo, hi) in enumerate(bounds):
+            o = outs[ch]
+            ctx.score_device(d_c[lo:hi], d_ref[lo:hi], min_ncc=THR, wid=w["wid"], out=o, stream=stream.cuda_stream)
+            rc = lib.mvs_compact_accepted(ctx._h, hi - lo, rank * n + lo, p(d_c[lo:hi]), p(d_n[lo:hi]), p(d_ref[lo:hi]),
+                                          p(o["vis_mask"]), p(o["avg"]), p(o["count"]), p(o["xy"]), None, BOUND,
+                                          p(records[lo:hi]), hi - lo, p(n_acc_ch[ch:ch + 1]), sp)
+            if rc != 0:
+                raise RuntimeError(lib.mvs_last_error().decode())
+            if world > 1:
+                ev = torch.cuda.Event()
+                ev.record(stream)
+                with torch.cuda.stream(comm):
+                    comm.wait_event(ev)
+                    dist.all_gather_into_tensor(counts_ch[ch], n_acc_ch[ch:ch + 1])
+                    counts_host[ch].copy_(counts_ch[ch], non_blocking=True)
+                    ev_counts = torch.cuda.Event()
+                    ev_counts.record(comm)
+                if pending is not None:
+                    gather_payload(*pending)
+                pending = (ch, ev_counts)
         if world > 1:
-            dist.all_gather_into_tensor(counts, n_acc)
-            mx = max(int(counts.max().item()), 1)                # host sync: payload size of this round
-            gathered = gbuf[: world * mx * rec_bytes].view(world * mx, rec_bytes)
-            dist.all_gather_into_tensor(gathered, records[:mx])
+            gather_payload(*pending)
+            stream.wait_stream(comm)                          # the step ends when every record has arrived
 
     def barrier():
         if world > 1:
@@ -360,7 +403,7 @@ def run_b200(args):
     if mode_b:
         kept = int((out["best_idx"] >= 0).sum().item())
     else:
-        kept = int(n_acc.item())
+        kept = int(n_acc_ch.sum().item())
 
     # ---- end to end through the C ABI with HOST buffers (pinned), copies inside the timed region
     mw = (V + 63) // 64
@@ -418,14 +461,14 @@ def run_b200(args):
                     "the binding units are the TEX pipe and FP32 issue (DESIGN.md)")
             step_desc = "score depth x normal sets + on-chip argmax (one winner per set leaves the SM)"
         else:
-            alg_bytes = n * (V * (2 * w["wid"] + 1) ** 2 + 28 + 8 * mw + 28)
+            alg_bytes = (n // NCH) * (V * (2 * w["wid"] + 1) ** 2 + 28 + 8 * mw + 28)   # per K1 launch
             kname = f"ncc_score_gather<{w['wid']},{16 if V <= 64 else 32}>"
             note = ("hypotheses are tile-ordered, so window bytes are served by L1/L2 and each is reused by several "
                     "hypotheses: frac compares ALGORITHMIC bytes/s with the HBM copy peak as the contract prescribes and "
                     "may exceed 1; the binding units are L1 wavefronts and instruction issue (DESIGN.md)")
             step_desc = "project + tile-order + score + compact accepted"
         if world > 1:
-            step_desc += " + NCCL all-gather"
+            step_desc += " + NCCL all-gather" + (f" ({NCH} chunks, gather of chunk i overlapped with scoring of chunk i+1)" if NCH > 1 else "")
         achieved = alg_bytes / (k_ms * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": world * n * args.steps / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world,
@@ -437,7 +480,7 @@ def run_b200(args):
                        "step": step_desc, "kept_per_gpu_last_step": kept},
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(wl), "peak_source": peak_src,
-                         "kernel_ms": k_ms, "kernel_launches_timed": k_n, "algorithmic_bytes_per_launch": alg_bytes,
+                         "kernel_ms": k_ms, "kernel_launches_timed": k_n, "algorithmic_bytes_per_launch": alg_bytes, "kernel_launches_per_step": NCH,
                          "note": note},
             "e2e": {"value": world * n * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": in_bytes,
                     "d2h_bytes_per_step": out_bytes,
