@@ -91,10 +91,11 @@ def test_other_window_sizes_against_oracle(golden, built_lib, wid):
     _compare(out, o["vis"], o["ncc"], o["avg"], V)
 
 
-@pytest.mark.parametrize("V,H,W", [(48, 480, 640), (70, 120, 200), (33, 97, 131)])
+@pytest.mark.parametrize("V,H,W", [(48, 480, 640), (70, 120, 200), (33, 97, 131), (130, 120, 160), (7, 120, 160), (260, 120, 160)])
 def test_synthetic_ring_against_oracle(built_lib, V, H, W):
     """48-view 640x480 is the shape the headline metric is quoted on; 70 views needs two
-    mask words; 33 x 97 x 131 has a row pitch that is not the image width."""
+    mask words; 33 x 97 x 131 has a view count and a width that are not multiples of 4; 130 and 260
+    views take the 32-lane kernel through 2 and 3 passes of 128 views; 7 views the 4-lane one."""
     import mvs_b200
     from mvs_b200 import rings
     from oracle import mode_a
@@ -160,3 +161,14 @@ def test_full_size_properties(built_lib):
         o = mode_a.score(mode_a.gray_from_rgb(rgb), cams, c[sub], ref[sub], 0.7)
         assert np.array_equal(vis[sub], o["vis"])
         assert np.abs(avg[sub] - o["avg"]).max() < AVG_TOL
+        # batch-composition invariance: a small batch takes the unsorted, unpaired path of the kernel and
+        # must give bit-identical results to the same hypotheses inside the tile-ordered 2^20 batch
+        small = ctx.score_device(dc[:5000].contiguous(), dref[:5000].contiguous(), min_ncc=0.7)
+        torch.cuda.synchronize()
+        for k in ("vis_mask", "count", "avg", "xy"):
+            assert torch.equal(small[k], out[k][:5000]), k
+        # idempotence: scoring twice changes nothing (no state leaks between calls)
+        again = ctx.score_device(dc, dref, min_ncc=0.7)
+        torch.cuda.synchronize()
+        for k in ("vis_mask", "count", "avg", "xy"):
+            assert torch.equal(again[k], out[k]), k
