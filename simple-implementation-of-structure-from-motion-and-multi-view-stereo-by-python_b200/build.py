@@ -10,7 +10,8 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(HERE, "libmvsncc.so")
 SOURCES = ["mvs_api.cu", "ncc_refexact.cu", "ncc_pmvs.cu", "bin.cu", "compact.cu", "scan.cu", "expand.cu", "ncc_pairs.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC"]
+OBJ_DIR = os.path.join(HERE, "build")
 
 
 def _nvcc():
@@ -29,18 +30,31 @@ def stale():
 
 
 def build(force=False, verbose=False):
-    """Compile every CUDA source of the library.  Returns the path of the .so."""
+    """Compile every CUDA source of the library (one nvcc per source, in parallel) and link.
+    Returns the path of the .so."""
     if not force and not stale():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-I", INCLUDE, "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
-    if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
-    res = subprocess.run(cmd, capture_output=True, text=True)
+    from concurrent.futures import ThreadPoolExecutor
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    nvcc = _nvcc()
+
+    def compile_one(src):
+        obj = os.path.join(OBJ_DIR, os.path.splitext(src)[0] + ".o")
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-I", INCLUDE, "-c", "-o", obj,
+                                                                               os.path.join(CSRC, src)]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        return src, obj, res
+
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as ex:
+        results = list(ex.map(compile_one, SOURCES))
+    for src, obj, res in results:
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed on %s:\n%s%s" % (src, res.stdout, res.stderr))
+        if verbose:
+            print(res.stderr)
+    res = subprocess.run([nvcc, "-shared", "-o", LIB] + [obj for _, obj, _ in results], capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
+        raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
     return LIB
 
 

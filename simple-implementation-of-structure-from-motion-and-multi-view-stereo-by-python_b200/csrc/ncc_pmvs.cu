@@ -24,6 +24,7 @@
 // Tensor cores are not used: a gather-bound reduction has no dense contraction.
 #include "project.cuh"
 #include "scan.cuh"
+#include <stdlib.h>
 
 #define FULL 0xffffffffu
 #define PMVS_VAR_MIN (1e-3f / 65025.0f)        // oracle/mode_b.py VAR_MIN in (grey/255)^2
@@ -136,8 +137,8 @@ __device__ __forceinline__ float tap4(cudaTextureObject_t tex, float u0, float v
     return fmaf(fv, bot - top, top);
 }
 
-template <int MU, bool REDUCE_A>
-__global__ void __launch_bounds__(32, 16) ncc_score_pmvs(const PmvsArgs A, int64_t N) {
+template <int MU, bool REDUCE_A, int MINB>
+__global__ void __launch_bounds__(32, MINB) ncc_score_pmvs(const PmvsArgs A, int64_t N) {
     constexpr int NS = MU * MU;
     constexpr int SPL = (NS + 31) / 32;                    // samples per lane
     constexpr float HALF = 0.5f * (MU - 1);
@@ -558,12 +559,21 @@ int mvs_launch_score_pmvs(mvs_ctx* ctx, int64_t N, const double* c, const double
     if (blocks > cap) blocks = cap;
     const int pslot = (int)(ctx->prof_n % MVS_PROF_RING);
     if (ctx->profile) MVS_CUDA_CHECK(cudaEventRecord(ctx->prof_ev[2 * pslot], s));
-#define PMVS_LAUNCH(MU_)                                                     \
-    case MU_:                                                                \
-        if (flags & MVS_PMVS_REDUCE_TO_REFEXACT)                             \
-            ncc_score_pmvs<MU_, true><<<(int)blocks, 32, 0, s>>>(A, N);      \
-        else                                                                 \
-            ncc_score_pmvs<MU_, false><<<(int)blocks, 32, 0, s>>>(A, N);     \
+    static int minb = -1;                                  // MVS_K2_MINB: resident warps per SM (tuning knob)
+    if (minb < 0) {
+        const char* e = getenv("MVS_K2_MINB");
+        minb = e ? atoi(e) : 16;
+    }
+#define PMVS_LAUNCH(MU_)                                                         \
+    case MU_:                                                                    \
+        if (flags & MVS_PMVS_REDUCE_TO_REFEXACT)                                 \
+            ncc_score_pmvs<MU_, true, 16><<<(int)blocks, 32, 0, s>>>(A, N);      \
+        else if (minb == 20)                                                     \
+            ncc_score_pmvs<MU_, false, 20><<<(int)blocks, 32, 0, s>>>(A, N);     \
+        else if (minb == 24)                                                     \
+            ncc_score_pmvs<MU_, false, 24><<<(int)blocks, 32, 0, s>>>(A, N);     \
+        else                                                                     \
+            ncc_score_pmvs<MU_, false, 16><<<(int)blocks, 32, 0, s>>>(A, N);     \
         break;
     switch (mu) {
         PMVS_LAUNCH(3) PMVS_LAUNCH(5) PMVS_LAUNCH(7) PMVS_LAUNCH(9) PMVS_LAUNCH(11)
