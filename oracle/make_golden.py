@@ -349,8 +349,33 @@ def make_tracks():
         for cam, x, y in ls.point2d_list:
             obs.append((float(cam), float(x), float(y)))
         offs.append(len(obs))
-    np.savez_compressed(os.path.join(GOLD, "dino_tracks.npz"), obs=np.array(obs), offsets=np.array(offs, dtype=np.int64))
-    return len(offs) - 1, len(obs)
+    # the reference's own seed stage (MVS2.py:208-260) on exactly these tracks: run its
+    # DensePointsWithMVS2 with the expansion and the PLY export stubbed out and keep the
+    # initial patches it hands to patch_expansion (MVS2.py:276)
+    seeds = []
+    orig_exp, orig_ply = ref_mvs2.patch_expansion, ref_mvs2.export2ply
+    ref_mvs2.patch_expansion = lambda a, im, initial, cells, cam_pos, bound: seeds.extend(initial)
+    ref_mvs2.export2ply = lambda *a, **k: None
+    try:
+        import warnings
+        with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ref_mvs2.DensePointsWithMVS2(imgs, gs, args)
+    finally:
+        ref_mvs2.patch_expansion, ref_mvs2.export2ply = orig_exp, orig_ply
+    V = len(imgs)
+    svis = np.zeros((len(seeds), V), dtype=bool)
+    sxy = np.zeros((len(seeds), 2))
+    for k, p in enumerate(seeds):
+        for v, x, y in p.V:
+            svis[k, int(v)] = True
+            sxy[k] = (x, y)
+    np.savez_compressed(os.path.join(GOLD, "dino_tracks.npz"), obs=np.array(obs), offsets=np.array(offs, dtype=np.int64),
+                        seed_c=np.array([p.c for p in seeds]), seed_n=np.array([p.n for p in seeds]),
+                        seed_ref=np.array([p.R for p in seeds], dtype=np.int32), seed_vis=svis, seed_xy=sxy,
+                        seed_avg=np.array([p.avg_ncc_score for p in seeds]),
+                        seed_color=np.array([np.asarray(p.color) for p in seeds], dtype=np.uint8))
+    return len(offs) - 1, len(obs), len(seeds)
 
 
 def main():
@@ -364,7 +389,7 @@ def main():
         raise SystemExit("reference not mounted at /root/reference: golden vectors can only be made in the build container")
     os.makedirs(GOLD, exist_ok=True)
     if a.tracks:
-        print("dino_tracks: %d tracks, %d observations" % make_tracks())
+        print("dino_tracks: %d tracks, %d observations, %d reference seed patches" % make_tracks())
         return
     ref_mvs2, ref_main = import_reference()
     imgs, par_text = load_dino(ref_main)
