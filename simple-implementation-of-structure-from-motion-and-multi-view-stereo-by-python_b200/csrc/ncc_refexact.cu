@@ -240,7 +240,7 @@ struct ScoreArgs {
 // i.e. the same (row, (col - WID) >> 2): they read exactly the same 16-byte quads of every
 // view, so each quad is loaded ONCE and multiplied against NB reference windows.  GS is the
 // compile-time byte stride between pixel groups (4*Vp) or 0 = read it from the arguments.
-template <int WID, int LPH, int NB, int GS>
+template <int WID, int LPH, int NB, int GS, bool WANT_NCC>
 __device__ __forceinline__ void score_block(const ScoreArgs& A, const uint32_t (&anchor)[NB], const int64_t (&h)[NB],
                                             uint32_t (*sref)[2 * WID + 1][(2 * WID + 7) / 4], int lih, uint32_t hmask) {
     constexpr int K = 2 * WID + 1;
@@ -250,6 +250,7 @@ __device__ __forceinline__ void score_block(const ScoreArgs& A, const uint32_t (
     const int mask_words32 = 2 * ((A.V + 63) >> 6);        // 32-bit chunks per hypothesis in vis_out
     const int passes = (LPH == 32) ? (A.Q + 31) >> 5 : 1;
     const double cn = (double)NPIX / (double)(NPIX - 1);
+    const double thr = A.thr;
 
     const int row = (int)(anchor[0] >> 16);
     const int cg = ((int)(anchor[0] & 0xffffu) - WID) >> 2;
@@ -354,22 +355,53 @@ __device__ __forceinline__ void score_block(const ScoreArgs& A, const uint32_t (
         for (int b = 0; b < NB; ++b) {
             const int Sv[4] = {(int)(s2[b].x & 0xffffu), (int)(s2[b].x >> 16), (int)(s2[b].y & 0xffffu), (int)(s2[b].y >> 16)};
             const uint32_t var[4] = {v4[b].x, v4[b].y, v4[b].z, v4[b].w};
-            float* nrow = (A.ncc_out && act) ? A.ncc_out + h[b] * A.V + 4 * qq : nullptr;
-            uint32_t nib = 0;
+            // views this lane may score: inside V (padding views have zero variance anyway), not the
+            // reference view itself, and only when the reference window has variance
+            uint32_t okmask = (act && var_r[b] != 0.0) ? 0xfu : 0u;
+            if ((r[b] >> 2) == qq) okmask &= ~(1u << (r[b] & 3));
+            if (4 * qq + 3 >= A.V) okmask &= (1u << max(A.V - 4 * qq, 0)) - 1u;
+            auto numerator = [&](int k) {
+                // exact integers: n*SAB, S*Sr <= 225^2 * 255^2 need 64 bits at wid > 5
+                return (WID <= 5) ? s32_to_double(NPIX * SAB[b][k] - Sv[k] * Sr[b])
+                                  : (double)((long long)NPIX * SAB[b][k] - (long long)Sv[k] * Sr[b]);
+            };
+            uint32_t near = 0u, nib = 0u;
+            float dump[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const int v = 4 * qq + k;
-                // exact integers: n*SAB, S*Sr <= 225^2 * 255^2 need 64 bits at wid > 5
-                const double num = (WID <= 5) ? s32_to_double(NPIX * SAB[b][k] - Sv[k] * Sr[b])
-                                              : (double)((long long)NPIX * SAB[b][k] - (long long)Sv[k] * Sr[b]);
-                const double var_i = u32_to_double(var[k]);
-                double val = ncc_fast(num, var_i, var_rs[b]);
-                const bool scored = act && (v < A.V) && (v != r[b]) && (var[k] != 0u) && (var_r[b] != 0.0);
-                if (__builtin_expect(scored && fabs(val - A.thr) < 1e-9, 0)) val = ncc_exact(num, var_i, var_r[b], cn);
-                const bool vis = scored && (val > A.thr);
+                const double val = ncc_fast(numerator(k), u32_to_double(var[k]), var_rs[b]);
+                if (var[k] == 0u) okmask &= ~(1u << k);
+                const bool vis = ((okmask >> k) & 1u) && (val > thr);
                 acc[b] += vis ? val : 0.0;
                 nib |= vis ? (1u << k) : 0u;
-                if (nrow && v < A.V) nrow[k] = scored ? (float)val : nanf("");
+                if (fabs(val - thr) < 1e-9) near |= 1u << k;
+                if constexpr (WANT_NCC) dump[k] = (float)val;
+            }
+            near &= okmask;
+            if (__builtin_expect(near != 0u, 0)) {
+                // rare: a value within 1e-9 of the threshold is redone with the correctly rounded sqrt and
+                // division and the provisional decision / sum contribution replaced
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (!((near >> k) & 1u)) continue;
+                    const double num = numerator(k), vd = u32_to_double(var[k]);
+                    const double fast = ncc_fast(num, vd, var_rs[b]);
+                    const double exact = ncc_exact(num, vd, var_r[b], cn);
+                    if ((nib >> k) & 1u) acc[b] -= fast;
+                    nib &= ~(1u << k);
+                    if (exact > thr) {
+                        acc[b] += exact;
+                        nib |= 1u << k;
+                    }
+                    if constexpr (WANT_NCC) dump[k] = (float)exact;
+                }
+            }
+            if constexpr (WANT_NCC) {
+                if (act) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (4 * qq + k < A.V) A.ncc_out[h[b] * A.V + 4 * qq + k] = ((okmask >> k) & 1u) ? dump[k] : nanf("");
+                }
             }
             // the lane group covers LPH*4 mask bits per pass = max(LPH/8, 1) 32-bit words
             constexpr int WPP = LPH >= 8 ? LPH / 8 : 1;
@@ -404,7 +436,7 @@ __device__ __forceinline__ void score_block(const ScoreArgs& A, const uint32_t (
 // (MVS_ANCHOR_INVALID: rejected, result already written by bin_project); order[i] =
 // hypothesis index (NULL: identity).
 // ---------------------------------------------------------------------------------
-template <int WID, int LPH, int GS, int MINB>
+template <int WID, int LPH, int GS, int MINB, bool WANT_NCC>
 __global__ void __launch_bounds__(256, MINB)
     ncc_score_gather(const ScoreArgs A, int64_t N, const uint32_t* __restrict__ anchors, const int32_t* __restrict__ order) {
     constexpr int K = 2 * WID + 1;
@@ -435,7 +467,7 @@ __global__ void __launch_bounds__(256, MINB)
             if (same) {
                 const uint32_t aa[2] = {a0, a1};
                 const int64_t hh[2] = {h0, h1};
-                score_block<WID, LPH, 2, GS>(A, aa, hh, sref, lih, hmask);
+                score_block<WID, LPH, 2, GS, WANT_NCC>(A, aa, hh, sref, lih, hmask);
             } else {
                 const uint32_t a2[2] = {a0, a1};
                 const int64_t h2[2] = {h0, h1};
@@ -444,7 +476,7 @@ __global__ void __launch_bounds__(256, MINB)
                     if (a2[t] == MVS_ANCHOR_INVALID) continue;
                     const uint32_t aa[1] = {a2[t]};
                     const int64_t hh[1] = {h2[t]};
-                    score_block<WID, LPH, 1, GS>(A, aa, hh, sref, lih, hmask);
+                    score_block<WID, LPH, 1, GS, WANT_NCC>(A, aa, hh, sref, lih, hmask);
                 }
             }
         }
@@ -458,7 +490,8 @@ __global__ void __launch_bounds__(256, MINB)
 template <int WID, int LPH, int GS, int MINB = MVS_K1_MINB>
 static int launch_gather_gs(mvs_ctx* ctx, const ScoreArgs& A, int64_t N, const uint32_t* anchors, const int32_t* order,
                             cudaStream_t s) {
-    auto kern = ncc_score_gather<WID, LPH, GS, MINB>;
+    // the per-view NCC dump is a parity/debug output: its stores are compiled out of the hot variant
+    auto kern = A.ncc_out ? ncc_score_gather<WID, LPH, GS, MINB, true> : ncc_score_gather<WID, LPH, GS, MINB, false>;
     const int64_t chunk = 8 * (32 / LPH) * 2 * 4;
     const int64_t want = (N + chunk - 1) / chunk;
     const int64_t cap = (int64_t)ctx->sm_count * MINB * 8;
