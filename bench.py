@@ -312,7 +312,7 @@ def run_b200(args):
     # then payload, on a second stream) overlapping the scoring of chunk i+1 (BENCH_EXCHANGE_CHUNKS).
     # Measured at N = 2: 4 chunks are SLOWER (1.31 vs 0.88 ms/step: quarter-size K1 launches lose their
     # L1 reuse and share the SMs with the NCCL kernels), so the default is one chunk = one all-gather per round.
-    NCH = int(os.environ.get("BENCH_EXCHANGE_CHUNKS", "1")) if (world > 1 and not mode_b) else 1
+    NCH = int(os.environ.get("BENCH_EXCHANGE_CHUNKS", "1")) if (world > 1 and not mode_b) else 1   # NCCL path only
     bounds = [(n * i // NCH, n * (i + 1) // NCH) for i in range(NCH)]
     comm = torch.cuda.Stream(device=dev) if world > 1 else None
     n_acc_ch = torch.zeros(NCH, dtype=torch.int64, device=dev)
@@ -329,6 +329,28 @@ def run_b200(args):
     if not mode_b:
         out, outs = make_outs()
 
+    # N > 1, Mode A, default: the compaction is FUSED with the all-gather -- mvs_compact_accepted_p2p stores
+    # this rank's records straight into every GPU's inbox over NVLink (symmetric memory), bracketed by two
+    # device-side barriers; no collective call, no host round trip for the payload size.  BENCH_EXCHANGE=nccl
+    # selects the counts + payload all-gather through NCCL instead (the baseline it replaces).
+    exchange = "none"
+    p2p = None
+    if world > 1 and not mode_b:
+        exchange = os.environ.get("BENCH_EXCHANGE", "p2p")
+        if exchange == "p2p":
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                inbox = symm_mem.empty(world * n * rec_bytes, dtype=torch.uint8, device=dev)
+                inbox_cnt = symm_mem.empty(world, dtype=torch.int64, device=dev)
+                h_rec = symm_mem.rendezvous(inbox, dist.group.WORLD)
+                h_cnt = symm_mem.rendezvous(inbox_cnt, dist.group.WORLD)
+                p2p = dict(inbox=inbox, cnt=inbox_cnt, h=h_rec, h2=h_cnt,
+                           recs=(C.c_void_p * world)(*[int(x) for x in h_rec.buffer_ptrs]),
+                           cnts=(C.c_void_p * world)(*[int(x) for x in h_cnt.buffer_ptrs]))
+            except Exception as e:                            # symmetric memory unavailable on this box
+                exchange = "nccl (symmetric memory unavailable: %s)" % type(e).__name__
+                p2p = None
+
     def gather_payload(ch, ev_counts):
         lo, hi = bounds[ch]
         ev_counts.synchronize()                               # host: this chunk's counts (later chunks are already enqueued)
@@ -344,6 +366,16 @@ def run_b200(args):
             if world > 1:
                 dist.all_gather_into_tensor(g_idx, out["best_idx"])
                 dist.all_gather_into_tensor(g_avg, out["best_avg"])
+            return
+        if p2p is not None:
+            p2p["h"].barrier(channel=0)                       # every inbox is free again
+            ctx.score_device(d_c, d_ref, min_ncc=THR, wid=w["wid"], out=out, stream=stream.cuda_stream)
+            rc = lib.mvs_compact_accepted_p2p(ctx._h, n, rank * n, p(d_c), p(d_n), p(d_ref), p(out["vis_mask"]), p(out["avg"]),
+                                              p(out["count"]), p(out["xy"]), None, BOUND, p2p["recs"], p2p["cnts"], rank, world,
+                                              n, sp)
+            if rc != 0:
+                raise RuntimeError(lib.mvs_last_error().decode())
+            p2p["h"].barrier(channel=1)                       # every rank's records and counts have landed
             return
         pending = None
         for ch, (lo, hi) in enumerate(bounds):
@@ -403,7 +435,23 @@ def run_b200(args):
     if mode_b:
         kept = int((out["best_idx"] >= 0).sum().item())
     else:
-        kept = int(n_acc_ch.sum().item())
+        kept = int(p2p["cnt"][rank].item()) if p2p is not None else int(n_acc_ch.sum().item())
+
+    # ---- the fused exchange really delivered: every peer's region in MY inbox has the checksum its sender reports
+    exchange_ok = None
+    if p2p is not None:
+        cnts = p2p["cnt"].clone()
+        def region_sum(r):
+            k = int(cnts[r].item())
+            reg = p2p["inbox"][r * n * rec_bytes: r * n * rec_bytes + k * rec_bytes]
+            return reg.view(torch.int64).sum().reshape(1)
+        mine = region_sum(rank)
+        sums = torch.zeros(world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(sums, mine)
+        got = torch.cat([region_sum(r) for r in range(world)])
+        okt = torch.tensor([int(torch.equal(sums, got) and int(cnts.min().item()) > 0)], device=dev)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        exchange_ok = bool(okt.item())
 
     # ---- end to end through the C ABI with HOST buffers (pinned), copies inside the timed region
     mw = (V + 63) // 64
@@ -467,7 +515,9 @@ def run_b200(args):
                     "hypotheses: frac compares ALGORITHMIC bytes/s with the HBM copy peak as the contract prescribes and "
                     "may exceed 1; the binding units are L1 wavefronts and instruction issue (DESIGN.md)")
             step_desc = "project + tile-order + score + compact accepted"
-        if world > 1:
+        if world > 1 and p2p is not None:
+            step_desc += " fused with the all-gather (P2P stores into every GPU's inbox over NVLink, two device-side barriers)"
+        elif world > 1:
             step_desc += " + NCCL all-gather" + (f" ({NCH} chunks, gather of chunk i overlapped with scoring of chunk i+1)" if NCH > 1 else "")
         achieved = alg_bytes / (k_ms * 1e-3) / 1e9
         line = {
@@ -477,7 +527,8 @@ def run_b200(args):
             "config": {"workload": workload_name(wl, n), "name": wl, "hypotheses_per_gpu": n, "views": V, "image": [H, W],
                        "mode": w["mode"],
                        "l2": "flushed between timed steps by a 256 MiB fill (not timed); per-step CUDA events summed",
-                       "step": step_desc, "kept_per_gpu_last_step": kept},
+                       "step": step_desc, "exchange": exchange, "exchange_verified": exchange_ok,
+                       "kept_per_gpu_last_step": kept},
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(wl), "peak_source": peak_src,
                          "kernel_ms": k_ms, "kernel_launches_timed": k_n, "algorithmic_bytes_per_launch": alg_bytes, "kernel_launches_per_step": NCH,

@@ -182,6 +182,24 @@ int mvs_compact_accepted(mvs_ctx* ctx, int64_t N, int64_t index_base, const doub
                          int64_t* n_out, void* stream);
 
 /*
+ * The same compaction FUSED with the per-round all-gather over peer memory (NVLink P2P stores):
+ * every GPU of the box owns an inbox of world * capacity records and world int64 counts; this
+ * rank's kept records are written, in input order, to region `rank` of EVERY inbox and its count to
+ * slot `rank` of every count array, from inside the compaction kernel -- no collective call, no host
+ * round trip for the payload size.  Replaces: mvs_compact_accepted followed by an all-gather of
+ * (counts, records); the reference has no counterpart (single process).
+ *   peer_records [world]  HOST array of DEVICE pointers, entry g = base of GPU g's inbox as mapped
+ *                         into THIS process (CUDA IPC / symmetric memory; entry `rank` = local)
+ *   peer_counts  [world]  likewise for the int64 count arrays
+ * The caller must order this call against the peers' use of their inboxes (a barrier across the
+ * GPUs before the call: inboxes free; after it: records visible).  Other pointers: DEVICE.
+ */
+int mvs_compact_accepted_p2p(mvs_ctx* ctx, int64_t N, int64_t index_base, const double* c, const double* nrm,
+                             const int32_t* ref, const uint64_t* vis_mask, const double* avg, const int32_t* count,
+                             const double* xy, const uint8_t* gate, int bound, void* const* peer_records,
+                             int64_t* const* peer_counts, int rank, int world, int64_t capacity, void* stream);
+
+/*
  * Cell table (CellTable, MVS2.py:80-120): one vacancy byte per (view, x-cell, y-cell),
  * shape [V, ceil((W-1)/cs), ceil((H-1)/cs)] exactly as the reference's list of bool
  * arrays (MVS2.py:88), 1 = vacant.  table_host NULL = all vacant.

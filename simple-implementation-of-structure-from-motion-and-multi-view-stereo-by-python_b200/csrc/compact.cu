@@ -13,6 +13,16 @@
 #include "mvs_common.cuh"
 
 #define TILE 1024          // hypotheses per CTA (256 threads x 4)
+
+// Destinations of the compacted records.  world == 1: the caller's own buffer.  world > 1: the
+// inbox of EVERY GPU of the box (peer-mapped pointers): this rank's records go to region `rank` of
+// each inbox, `capacity` records per region, and its count to slot `rank` of each count array -- the
+// compaction IS the all-gather (stores over NVLink), no collective call and no host round trip.
+struct PeerList {
+    uint8_t* rec[MVS_MAX_PEERS];
+    int64_t* cnt[MVS_MAX_PEERS];
+    int world, rank;
+};
 #define FULL 0xffffffffu
 
 __device__ __forceinline__ bool keep_flag(const int32_t* count, const uint8_t* gate, int bound, int64_t i, int64_t N) {
@@ -37,7 +47,7 @@ __global__ void __launch_bounds__(256) compact_count(const int32_t* __restrict__
 }
 
 // single CTA: exclusive scan of tile_counts[0..T) in place; total -> *n_out
-__global__ void __launch_bounds__(1024) compact_scan(int32_t* __restrict__ tile_counts, int T, int64_t* __restrict__ n_out) {
+__global__ void __launch_bounds__(1024) compact_scan(int32_t* __restrict__ tile_counts, int T, const PeerList P) {
     __shared__ int64_t carry;
     __shared__ int wsum[32];
     if (threadIdx.x == 0) carry = 0;
@@ -70,7 +80,7 @@ __global__ void __launch_bounds__(1024) compact_scan(int32_t* __restrict__ tile_
         if (threadIdx.x == 1023) carry = excl + v;
         __syncthreads();
     }
-    if (threadIdx.x == 0) *n_out = carry;
+    if (threadIdx.x < P.world) P.cnt[threadIdx.x][P.rank] = carry;   // every GPU learns this rank's count
 }
 
 // Records are assembled in shared memory (a kept hypothesis writes its own record there) and
@@ -79,7 +89,7 @@ __global__ void __launch_bounds__(256)
     compact_scatter(const int32_t* __restrict__ count, const uint8_t* __restrict__ gate, int bound, int64_t N,
                     const int32_t* __restrict__ tile_offsets, int64_t index_base, const double* __restrict__ c,
                     const double* __restrict__ nrm, const int32_t* __restrict__ ref, const uint64_t* __restrict__ vis,
-                    const double* __restrict__ avg, const double* __restrict__ xy, int mw, uint8_t* __restrict__ records,
+                    const double* __restrict__ avg, const double* __restrict__ xy, int mw, const PeerList P,
                     int rec_bytes, int64_t capacity, const int64_t* __restrict__ index_arr, const int32_t* __restrict__ px) {
     extern __shared__ __align__(16) uint8_t s_rec[];       // 256 records
     __shared__ int warp_base[8];
@@ -120,18 +130,21 @@ __global__ void __launch_bounds__(256)
         room = room < 0 ? 0 : room;
         const int nrec = (int)(room < total ? room : total);
         const int nwords = nrec * rec_words;
-        uint64_t* dst = reinterpret_cast<uint64_t*>(records + out * rec_bytes);
         const uint64_t* src = reinterpret_cast<const uint64_t*>(s_rec);
-        for (int t = threadIdx.x; t < nwords; t += 256) dst[t] = src[t];
+        const int64_t off = ((int64_t)P.rank * capacity + out) * rec_bytes;
+        for (int t = threadIdx.x; t < nwords; t += 256) {
+            const uint64_t wv = src[t];
+            for (int d = 0; d < P.world; ++d) reinterpret_cast<uint64_t*>(P.rec[d] + off)[t] = wv;
+        }
         out += total;
         __syncthreads();
     }
 }
 
-int mvs_launch_compact(mvs_ctx* ctx, int64_t N, int64_t index_base, const double* c, const double* nrm, const int32_t* ref,
-                       const uint64_t* vis, const double* avg, const int32_t* count, const double* xy, const uint8_t* gate,
-                       int bound, void* records, int64_t capacity, int64_t* d_n_out, const int64_t* index_arr,
-                       const int32_t* px, cudaStream_t s) {
+static int launch_compact_peers(mvs_ctx* ctx, int64_t N, int64_t index_base, const double* c, const double* nrm,
+                                const int32_t* ref, const uint64_t* vis, const double* avg, const int32_t* count,
+                                const double* xy, const uint8_t* gate, int bound, const PeerList& P, int64_t capacity,
+                                const int64_t* index_arr, const int32_t* px, cudaStream_t s) {
     const int T = (int)((N + TILE - 1) / TILE);
     if ((size_t)T * sizeof(int32_t) > ctx->tile_bytes) {
         if (ctx->d_tiles) cudaFree(ctx->d_tiles);
@@ -146,19 +159,50 @@ int mvs_launch_compact(mvs_ctx* ctx, int64_t N, int64_t index_base, const double
         ctx->tile_bytes = want;
     }
     const int mw = (ctx->V + 63) / 64;
-    if (T == 0) {
-        MVS_CUDA_CHECK(cudaMemsetAsync(d_n_out, 0, sizeof(int64_t), s));
-        return MVS_OK;
+    if (T > 0) {
+        compact_count<<<T, 256, 0, s>>>(count, gate, bound, N, ctx->d_tiles);
+        ctx->launches++;
     }
-    compact_count<<<T, 256, 0, s>>>(count, gate, bound, N, ctx->d_tiles);
-    compact_scan<<<1, 1024, 0, s>>>(ctx->d_tiles, T, d_n_out);
-    const int rec_bytes = (int)(sizeof(mvs_patch_record) + 8 * mw);
-    const size_t smem = (size_t)256 * rec_bytes;
-    if (smem > 48 * 1024)
-        MVS_CUDA_CHECK(cudaFuncSetAttribute(compact_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    compact_scatter<<<T, 256, smem, s>>>(count, gate, bound, N, ctx->d_tiles, index_base, c, nrm, ref, vis, avg, xy, mw,
-                                         (uint8_t*)records, rec_bytes, capacity, index_arr, px);
-    ctx->launches += 3;
+    compact_scan<<<1, 1024, 0, s>>>(ctx->d_tiles, T, P);          // T == 0: just publishes a zero count
+    ctx->launches++;
+    if (T > 0) {
+        const int rec_bytes = (int)(sizeof(mvs_patch_record) + 8 * mw);
+        const size_t smem = (size_t)256 * rec_bytes;
+        if (smem > 48 * 1024)
+            MVS_CUDA_CHECK(cudaFuncSetAttribute(compact_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        compact_scatter<<<T, 256, smem, s>>>(count, gate, bound, N, ctx->d_tiles, index_base, c, nrm, ref, vis, avg, xy, mw, P,
+                                             rec_bytes, capacity, index_arr, px);
+        ctx->launches++;
+    }
     MVS_CUDA_CHECK(cudaGetLastError());
     return MVS_OK;
+}
+
+int mvs_launch_compact(mvs_ctx* ctx, int64_t N, int64_t index_base, const double* c, const double* nrm, const int32_t* ref,
+                       const uint64_t* vis, const double* avg, const int32_t* count, const double* xy, const uint8_t* gate,
+                       int bound, void* records, int64_t capacity, int64_t* d_n_out, const int64_t* index_arr,
+                       const int32_t* px, cudaStream_t s) {
+    PeerList P;
+    memset(&P, 0, sizeof(P));
+    P.world = 1;
+    P.rank = 0;
+    P.rec[0] = (uint8_t*)records;
+    P.cnt[0] = d_n_out;
+    return launch_compact_peers(ctx, N, index_base, c, nrm, ref, vis, avg, count, xy, gate, bound, P, capacity, index_arr, px, s);
+}
+
+int mvs_launch_compact_p2p(mvs_ctx* ctx, int64_t N, int64_t index_base, const double* c, const double* nrm,
+                           const int32_t* ref, const uint64_t* vis, const double* avg, const int32_t* count,
+                           const double* xy, const uint8_t* gate, int bound, void* const* peer_records,
+                           int64_t* const* peer_counts, int rank, int world, int64_t capacity, cudaStream_t s) {
+    PeerList P;
+    memset(&P, 0, sizeof(P));
+    P.world = world;
+    P.rank = rank;
+    for (int d = 0; d < world; ++d) {
+        P.rec[d] = (uint8_t*)peer_records[d];
+        P.cnt[d] = peer_counts[d];
+    }
+    return launch_compact_peers(ctx, N, index_base, c, nrm, ref, vis, avg, count, xy, gate, bound, P, capacity, nullptr,
+                                nullptr, s);
 }

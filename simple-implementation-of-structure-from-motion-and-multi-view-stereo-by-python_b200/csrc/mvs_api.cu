@@ -406,6 +406,25 @@ extern "C" int mvs_score_batch(mvs_ctx* ctx, int mode, int64_t N, const double* 
     return MVS_OK;
 }
 
+extern "C" int mvs_compact_accepted_p2p(mvs_ctx* ctx, int64_t N, int64_t index_base, const double* c, const double* nrm,
+                                        const int32_t* ref, const uint64_t* vis_mask, const double* avg,
+                                        const int32_t* count, const double* xy, const uint8_t* gate, int bound,
+                                        void* const* peer_records, int64_t* const* peer_counts, int rank, int world,
+                                        int64_t capacity, void* stream) {
+    if (!ctx) { mvs_set_error("mvs_compact_accepted_p2p: null context"); return MVS_ERR_ARG; }
+    if (N < 0 || capacity < 0 || !peer_records || !peer_counts || world < 1 || world > MVS_MAX_PEERS || rank < 0 ||
+        rank >= world || (N > 0 && (!c || !ref || !vis_mask || !avg || !count || !xy))) {
+        mvs_set_error("mvs_compact_accepted_p2p: need 1 <= world <= %d, 0 <= rank < world, the peer tables and c, ref, "
+                      "vis_mask, avg, count, xy", MVS_MAX_PEERS);
+        return MVS_ERR_ARG;
+    }
+    for (int d = 0; d < world; ++d)
+        if (!peer_records[d] || !peer_counts[d]) { mvs_set_error("mvs_compact_accepted_p2p: null peer pointer %d", d); return MVS_ERR_ARG; }
+    MVS_CUDA_CHECK(cudaSetDevice(ctx->device));
+    return mvs_launch_compact_p2p(ctx, N, index_base, c, nrm, ref, vis_mask, avg, count, xy, gate, bound, peer_records,
+                                  peer_counts, rank, world, capacity, (cudaStream_t)stream);
+}
+
 extern "C" int mvs_score_pmvs(mvs_ctx* ctx, int64_t N, const double* c, const double* nrm, const int32_t* ref,
                               const uint64_t* cand, double min_ncc, int mu, int flags, int group, int bound,
                               uint64_t* vis_mask, double* avg, int32_t* count, double* xy, float* ncc, int32_t* best_idx,

@@ -9,6 +9,7 @@
 
 #define MVS_ABI_VERSION 1
 #define MVS_GROUP_PAD 8
+#define MVS_MAX_PEERS 16
 #define MVS_PROF_RING 64
 #define MVS_ANCHOR_INVALID 0xffffffffu
 #define MVS_BIN_SHIFT 3          // anchor tiles of 8x8 pixels
@@ -143,6 +144,10 @@ int mvs_launch_score_pmvs(mvs_ctx* ctx, int64_t N, const double* c, const double
 int mvs_launch_select_best(mvs_ctx* ctx, int64_t N, int group, const double* avg, const int32_t* count, int bound,
                            int32_t* best_idx, double* best_avg, cudaStream_t s);
 void mvs_pmvs_release(mvs_ctx* ctx);
+int mvs_launch_compact_p2p(mvs_ctx* ctx, int64_t N, int64_t index_base, const double* c, const double* nrm,
+                           const int32_t* ref, const uint64_t* vis, const double* avg, const int32_t* count,
+                           const double* xy, const uint8_t* gate, int bound, void* const* peer_records,
+                           int64_t* const* peer_counts, int rank, int world, int64_t capacity, cudaStream_t s);
 int mvs_launch_compact(mvs_ctx* ctx, int64_t N, int64_t index_base, const double* c, const double* nrm, const int32_t* ref,
                        const uint64_t* vis, const double* avg, const int32_t* count, const double* xy, const uint8_t* gate,
                        int bound, void* records, int64_t capacity, int64_t* d_n_out, const int64_t* index_arr,

@@ -47,3 +47,49 @@ def test_compaction_matches_numpy(golden, built_lib, N, with_gate):
         assert np.array_equal(got["xy"], xy[idx]) and np.array_equal(got["avg"], avg[idx])
         assert np.array_equal(got["ref"], ref[idx]) and np.array_equal(got["count"], count[idx])
         assert np.array_equal(got["vis"], vis[idx])
+
+
+def test_fused_compaction_all_gather_layout(golden, built_lib):
+    """mvs_compact_accepted_p2p with two "GPUs" emulated by two inboxes on one device: rank r's records
+    land, in input order, in region r of EVERY inbox and its count in slot r of every count array --
+    the same bytes mvs_compact_accepted produces."""
+    import ctypes as C
+    import torch
+    import mvs_b200
+    from mvs_b200 import _lib
+    d = golden("dino12_scores")
+    lib = _lib.load()
+    with mvs_b200.MvsContext(d["rgb"], d["K"], d["R"], d["t"], Rrt=d["Rrt"]) as ctx:
+        rb = lib.mvs_record_bytes(ctx._h)
+        c = torch.from_numpy(d["c"]).cuda()
+        ref = torch.from_numpy(d["ref"]).cuda()
+        nrm = torch.zeros_like(c)
+        out = ctx.score_device(c, ref, min_ncc=0.4)
+        N = c.shape[0]
+        p = lambda x: C.c_void_p(x.data_ptr())
+        sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        want = torch.zeros((N, rb), dtype=torch.uint8, device="cuda")
+        n_want = torch.zeros(1, dtype=torch.int64, device="cuda")
+        assert lib.mvs_compact_accepted(ctx._h, N, 1000, p(c), p(nrm), p(ref), p(out["vis_mask"]), p(out["avg"]), p(out["count"]),
+                                        p(out["xy"]), None, 2, p(want), N, p(n_want), sp) == 0
+        world, cap = 2, N
+        inbox = [torch.zeros((world * cap, rb), dtype=torch.uint8, device="cuda") for _ in range(world)]
+        counts = [torch.full((world,), -1, dtype=torch.int64, device="cuda") for _ in range(world)]
+        recs = (C.c_void_p * world)(*[x.data_ptr() for x in inbox])
+        cnts = (C.c_void_p * world)(*[x.data_ptr() for x in counts])
+        for rank in range(world):
+            assert lib.mvs_compact_accepted_p2p(ctx._h, N, 1000, p(c), p(nrm), p(ref), p(out["vis_mask"]), p(out["avg"]),
+                                                p(out["count"]), p(out["xy"]), None, 2, recs, cnts, rank, world, cap, sp) == 0
+        torch.cuda.synchronize()
+        k = int(n_want.item())
+        assert 0 < k < N
+        for g in range(world):
+            assert counts[g].tolist() == [k, k]
+            for rank in range(world):
+                assert torch.equal(inbox[g][rank * cap: rank * cap + k], want[:k])
+                assert not inbox[g][rank * cap + k: (rank + 1) * cap].any()
+        # an empty batch publishes a zero count
+        assert lib.mvs_compact_accepted_p2p(ctx._h, 0, 0, None, None, None, None, None, None, None, None, 2, recs, cnts, 1,
+                                            world, cap, sp) == 0
+        torch.cuda.synchronize()
+        assert counts[0].tolist() == [k, 0] and counts[1].tolist() == [k, 0]
