@@ -340,11 +340,13 @@ def run_b200(args):
         if exchange == "p2p":
             try:
                 import torch.distributed._symmetric_memory as symm_mem
-                inbox = symm_mem.empty(world * n * rec_bytes, dtype=torch.uint8, device=dev)
+                wire = 0 if os.environ.get("BENCH_WIRE", "compact") == "full" else 1
+                wire_bytes = lib.mvs_wire_bytes(ctx._h, wire)
+                inbox = symm_mem.empty(world * n * wire_bytes, dtype=torch.uint8, device=dev)
                 inbox_cnt = symm_mem.empty(world, dtype=torch.int64, device=dev)
                 h_rec = symm_mem.rendezvous(inbox, dist.group.WORLD)
                 h_cnt = symm_mem.rendezvous(inbox_cnt, dist.group.WORLD)
-                p2p = dict(inbox=inbox, cnt=inbox_cnt, h=h_rec, h2=h_cnt,
+                p2p = dict(inbox=inbox, cnt=inbox_cnt, h=h_rec, h2=h_cnt, wire=wire, wire_bytes=wire_bytes,
                            recs=(C.c_void_p * world)(*[int(x) for x in h_rec.buffer_ptrs]),
                            cnts=(C.c_void_p * world)(*[int(x) for x in h_cnt.buffer_ptrs]))
             except Exception as e:                            # symmetric memory unavailable on this box
@@ -372,7 +374,7 @@ def run_b200(args):
             ctx.score_device(d_c, d_ref, min_ncc=THR, wid=w["wid"], out=out, stream=stream.cuda_stream)
             rc = lib.mvs_compact_accepted_p2p(ctx._h, n, rank * n, p(d_c), p(d_n), p(d_ref), p(out["vis_mask"]), p(out["avg"]),
                                               p(out["count"]), p(out["xy"]), None, BOUND, p2p["recs"], p2p["cnts"], rank, world,
-                                              n, sp)
+                                              p2p["wire"], n, sp)
             if rc != 0:
                 raise RuntimeError(lib.mvs_last_error().decode())
             p2p["h"].barrier(channel=1)                       # every rank's records and counts have landed
@@ -443,7 +445,8 @@ def run_b200(args):
         cnts = p2p["cnt"].clone()
         def region_sum(r):
             k = int(cnts[r].item())
-            reg = p2p["inbox"][r * n * rec_bytes: r * n * rec_bytes + k * rec_bytes]
+            wb_ = p2p["wire_bytes"]
+            reg = p2p["inbox"][r * n * wb_: r * n * wb_ + k * wb_]
             return reg.view(torch.int64).sum().reshape(1)
         mine = region_sum(rank)
         sums = torch.zeros(world, dtype=torch.int64, device=dev)
@@ -516,7 +519,8 @@ def run_b200(args):
                     "may exceed 1; the binding units are L1 wavefronts and instruction issue (DESIGN.md)")
             step_desc = "project + tile-order + score + compact accepted"
         if world > 1 and p2p is not None:
-            step_desc += " fused with the all-gather (P2P stores into every GPU's inbox over NVLink, two device-side barriers)"
+            step_desc += (" fused with the all-gather (P2P stores into every GPU's inbox over NVLink, two device-side barriers; "
+                          f"{p2p['wire_bytes']}-byte {'compact' if p2p['wire'] else 'full'} wire records)")
         elif world > 1:
             step_desc += " + NCCL all-gather" + (f" ({NCH} chunks, gather of chunk i overlapped with scoring of chunk i+1)" if NCH > 1 else "")
         achieved = alg_bytes / (k_ms * 1e-3) / 1e9

@@ -46,6 +46,15 @@ extern "C" {
                                          around (int(x), int(y)), no interpolation, the bounds rule of
                                          HarrisFeatures.py:128 -- must agree with MVS_MODE_REFEXACT */
 
+/* record formats on the wire between GPUs (mvs_compact_accepted_p2p, mvs_records_expand) */
+#define MVS_WIRE_FULL 0    /* mvs_patch_record + visible mask: mvs_record_bytes() */
+#define MVS_WIRE_COMPACT 1 /* only what a peer cannot recompute -- c[3] f64, avg f64, index i64, ref i32,
+                              px[2] i32, pad i32, visible mask: 56 + 8*ceil(V/64) bytes.  Valid for patches
+                              whose normal is the unit vector from c to their reference camera and whose
+                              x, y is the reference projection of c, i.e. every patch the reference's MVS
+                              creates (MVS2.py:247, 357-358, 74); mvs_records_expand rebuilds n, xy and
+                              count bit-identically on the receiving GPU */
+
 typedef struct mvs_ctx mvs_ctx;
 
 /* ABI version of this header (checked by the Python loader). */
@@ -191,13 +200,24 @@ int mvs_compact_accepted(mvs_ctx* ctx, int64_t N, int64_t index_base, const doub
  *   peer_records [world]  HOST array of DEVICE pointers, entry g = base of GPU g's inbox as mapped
  *                         into THIS process (CUDA IPC / symmetric memory; entry `rank` = local)
  *   peer_counts  [world]  likewise for the int64 count arrays
+ *   wire                  MVS_WIRE_FULL | MVS_WIRE_COMPACT: record format written (region stride =
+ *                         capacity * mvs_wire_bytes(ctx, wire)); nrm, xy are not read for COMPACT
  * The caller must order this call against the peers' use of their inboxes (a barrier across the
  * GPUs before the call: inboxes free; after it: records visible).  Other pointers: DEVICE.
  */
 int mvs_compact_accepted_p2p(mvs_ctx* ctx, int64_t N, int64_t index_base, const double* c, const double* nrm,
                              const int32_t* ref, const uint64_t* vis_mask, const double* avg, const int32_t* count,
                              const double* xy, const uint8_t* gate, int bound, void* const* peer_records,
-                             int64_t* const* peer_counts, int rank, int world, int64_t capacity, void* stream);
+                             int64_t* const* peer_counts, int rank, int world, int wire, int64_t capacity, void* stream);
+
+/* Bytes per record of a wire format for this context (0: unknown format). */
+int mvs_wire_bytes(const mvs_ctx* ctx, int wire);
+
+/*
+ * Receiver side: rebuild n full patch records (mvs_record_bytes() each) from wire records.
+ * DEVICE pointers; enqueued on `stream`.  MVS_WIRE_FULL is a plain copy.
+ */
+int mvs_records_expand(mvs_ctx* ctx, int wire, const void* wire_records, int64_t n, void* records, void* stream);
 
 /*
  * Cell table (CellTable, MVS2.py:80-120): one vacancy byte per (view, x-cell, y-cell),

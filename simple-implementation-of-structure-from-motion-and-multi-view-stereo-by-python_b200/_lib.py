@@ -20,7 +20,9 @@ SYMBOLS = {
     "mvs_score_batch": (C.c_int, [_P, C.c_int, C.c_int64, _P, _P, _P, C.c_double, C.c_int, _P, _P, _P, _P, _P,
                                   C.c_int, _P]),
     "mvs_compact_accepted_p2p": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, _P, _P, C.c_int,
-                                           C.c_int, C.c_int64, _P]),
+                                           C.c_int, C.c_int, C.c_int64, _P]),
+    "mvs_wire_bytes": (C.c_int, [_P, C.c_int]),
+    "mvs_records_expand": (C.c_int, [_P, C.c_int, _P, C.c_int64, _P, _P]),
     "mvs_score_pmvs": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P,
                                  _P, _P, _P, _P, C.c_int, _P]),
     "mvs_select_best": (C.c_int, [_P, C.c_int64, C.c_int, _P, _P, C.c_int, _P, _P, _P]),

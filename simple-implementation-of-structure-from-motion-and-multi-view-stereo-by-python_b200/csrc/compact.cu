@@ -22,7 +22,21 @@ struct PeerList {
     uint8_t* rec[MVS_MAX_PEERS];
     int64_t* cnt[MVS_MAX_PEERS];
     int world, rank;
+    int wire;              // MVS_WIRE_FULL | MVS_WIRE_COMPACT: format of the records written
 };
+
+// MVS_WIRE_COMPACT: only what a peer cannot recompute.  Every patch the reference's MVS creates has
+// n = (O_ref - c)/|O_ref - c| (MVS2.py:247, 357-358) and carries the reference projection of c as its
+// x, y (MVS2.py:74); count = popcount(visible set).  56 + 8*ceil(V/64) bytes instead of 96 + 8*ceil(V/64).
+struct WireCompact {
+    double c[3];
+    double avg;
+    int64_t index;
+    int32_t ref;
+    int32_t px[2];
+    int32_t pad;
+};
+static_assert(sizeof(WireCompact) == 56, "wire layout");
 #define FULL 0xffffffffu
 
 __device__ __forceinline__ bool keep_flag(const int32_t* count, const uint8_t* gate, int bound, int64_t i, int64_t N) {
@@ -108,7 +122,19 @@ __global__ void __launch_bounds__(256)
             if (q < w) before += warp_base[q];
             total += warp_base[q];
         }
-        if (k) {
+        if (k && P.wire == MVS_WIRE_COMPACT) {
+            const int slot = before + __popc(b & ((1u << lane) - 1u));
+            WireCompact* r = reinterpret_cast<WireCompact*>(s_rec + (size_t)slot * rec_bytes);
+            r->c[0] = c[3 * i]; r->c[1] = c[3 * i + 1]; r->c[2] = c[3 * i + 2];
+            r->avg = avg[i];
+            r->index = index_arr ? index_arr[i] : index_base + i;
+            r->ref = ref[i];
+            r->px[0] = px ? px[2 * i] : -1;
+            r->px[1] = px ? px[2 * i + 1] : -1;
+            r->pad = 0;
+            uint64_t* rv = reinterpret_cast<uint64_t*>(r + 1);
+            for (int q = 0; q < mw; ++q) rv[q] = vis[i * mw + q];
+        } else if (k) {
             const int slot = before + __popc(b & ((1u << lane) - 1u));
             mvs_patch_record* r = reinterpret_cast<mvs_patch_record*>(s_rec + (size_t)slot * rec_bytes);
             r->c[0] = c[3 * i]; r->c[1] = c[3 * i + 1]; r->c[2] = c[3 * i + 2];
@@ -166,7 +192,7 @@ static int launch_compact_peers(mvs_ctx* ctx, int64_t N, int64_t index_base, con
     compact_scan<<<1, 1024, 0, s>>>(ctx->d_tiles, T, P);          // T == 0: just publishes a zero count
     ctx->launches++;
     if (T > 0) {
-        const int rec_bytes = (int)(sizeof(mvs_patch_record) + 8 * mw);
+        const int rec_bytes = (int)((P.wire == MVS_WIRE_COMPACT ? sizeof(WireCompact) : sizeof(mvs_patch_record)) + 8 * mw);
         const size_t smem = (size_t)256 * rec_bytes;
         if (smem > 48 * 1024)
             MVS_CUDA_CHECK(cudaFuncSetAttribute(compact_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -186,6 +212,7 @@ int mvs_launch_compact(mvs_ctx* ctx, int64_t N, int64_t index_base, const double
     memset(&P, 0, sizeof(P));
     P.world = 1;
     P.rank = 0;
+    P.wire = MVS_WIRE_FULL;
     P.rec[0] = (uint8_t*)records;
     P.cnt[0] = d_n_out;
     return launch_compact_peers(ctx, N, index_base, c, nrm, ref, vis, avg, count, xy, gate, bound, P, capacity, index_arr, px, s);
@@ -194,15 +221,72 @@ int mvs_launch_compact(mvs_ctx* ctx, int64_t N, int64_t index_base, const double
 int mvs_launch_compact_p2p(mvs_ctx* ctx, int64_t N, int64_t index_base, const double* c, const double* nrm,
                            const int32_t* ref, const uint64_t* vis, const double* avg, const int32_t* count,
                            const double* xy, const uint8_t* gate, int bound, void* const* peer_records,
-                           int64_t* const* peer_counts, int rank, int world, int64_t capacity, cudaStream_t s) {
+                           int64_t* const* peer_counts, int rank, int world, int wire, int64_t capacity, cudaStream_t s) {
     PeerList P;
     memset(&P, 0, sizeof(P));
     P.world = world;
     P.rank = rank;
+    P.wire = wire;
     for (int d = 0; d < world; ++d) {
         P.rec[d] = (uint8_t*)peer_records[d];
         P.cnt[d] = peer_counts[d];
     }
     return launch_compact_peers(ctx, N, index_base, c, nrm, ref, vis, avg, count, xy, gate, bound, P, capacity, nullptr,
                                 nullptr, s);
+}
+
+// ---------------------------------------------------------------------------------
+// Receiver side of MVS_WIRE_COMPACT: rebuild full patch records.  n = (O_ref - c)/|O_ref - c| with
+// the same correctly rounded operations as the candidate generator (expand.cu, MVS2.py:357-358),
+// x, y = the reference projection in cv2's operation order (project.cuh) -- bit-identical to what
+// the sender held.
+// ---------------------------------------------------------------------------------
+#include "project.cuh"
+
+__global__ void __launch_bounds__(256)
+    records_expand(const uint8_t* __restrict__ wire, int64_t n, int mw, const CamProj* __restrict__ cams,
+                   const CamGeom* __restrict__ geom, int V, uint8_t* __restrict__ records) {
+    const int wb = (int)sizeof(WireCompact) + 8 * mw, rb = (int)sizeof(mvs_patch_record) + 8 * mw;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const WireCompact* w = reinterpret_cast<const WireCompact*>(wire + i * wb);
+        mvs_patch_record* r = reinterpret_cast<mvs_patch_record*>(records + i * rb);
+        const int v = w->ref;
+        const double c0 = w->c[0], c1 = w->c[1], c2 = w->c[2];
+        r->c[0] = c0; r->c[1] = c1; r->c[2] = c2;
+        double x = nan(""), y = nan(""), n0 = 0.0, n1 = 0.0, n2 = 0.0;
+        if (v >= 0 && v < V) {
+            const CamGeom& g = geom[v];
+            const double q0 = __dsub_rn(g.C[0], c0), q1 = __dsub_rn(g.C[1], c1), q2 = __dsub_rn(g.C[2], c2);
+            const double dist = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(q0, q0), __dmul_rn(q1, q1)), __dmul_rn(q2, q2)));
+            n0 = __ddiv_rn(q0, dist); n1 = __ddiv_rn(q1, dist); n2 = __ddiv_rn(q2, dist);
+            project_ref(cams[v], c0, c1, c2, x, y);
+        }
+        r->n[0] = n0; r->n[1] = n1; r->n[2] = n2;
+        r->xy[0] = x; r->xy[1] = y;
+        r->avg = w->avg;
+        r->ref = v;
+        r->index = w->index;
+        r->px[0] = w->px[0];
+        r->px[1] = w->px[1];
+        const uint64_t* wv = reinterpret_cast<const uint64_t*>(w + 1);
+        uint64_t* rv = reinterpret_cast<uint64_t*>(r + 1);
+        int cnt = 0;
+        for (int q = 0; q < mw; ++q) {
+            rv[q] = wv[q];
+            cnt += __popcll(wv[q]);
+        }
+        r->count = cnt;
+    }
+}
+
+int mvs_launch_records_expand(mvs_ctx* ctx, const void* wire, int64_t n, void* records, cudaStream_t s) {
+    if (n == 0) return MVS_OK;
+    int64_t blocks = (n + 255) / 256;
+    const int64_t cap = (int64_t)ctx->sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    records_expand<<<(int)blocks, 256, 0, s>>>((const uint8_t*)wire, n, (ctx->V + 63) / 64, ctx->d_cam, ctx->d_geom, ctx->V,
+                                               (uint8_t*)records);
+    ctx->launches++;
+    MVS_CUDA_CHECK(cudaGetLastError());
+    return MVS_OK;
 }

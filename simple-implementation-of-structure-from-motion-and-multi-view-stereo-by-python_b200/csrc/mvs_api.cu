@@ -410,8 +410,9 @@ extern "C" int mvs_compact_accepted_p2p(mvs_ctx* ctx, int64_t N, int64_t index_b
                                         const int32_t* ref, const uint64_t* vis_mask, const double* avg,
                                         const int32_t* count, const double* xy, const uint8_t* gate, int bound,
                                         void* const* peer_records, int64_t* const* peer_counts, int rank, int world,
-                                        int64_t capacity, void* stream) {
+                                        int wire, int64_t capacity, void* stream) {
     if (!ctx) { mvs_set_error("mvs_compact_accepted_p2p: null context"); return MVS_ERR_ARG; }
+    if (wire != MVS_WIRE_FULL && wire != MVS_WIRE_COMPACT) { mvs_set_error("mvs_compact_accepted_p2p: unknown wire format %d", wire); return MVS_ERR_ARG; }
     if (N < 0 || capacity < 0 || !peer_records || !peer_counts || world < 1 || world > MVS_MAX_PEERS || rank < 0 ||
         rank >= world || (N > 0 && (!c || !ref || !vis_mask || !avg || !count || !xy))) {
         mvs_set_error("mvs_compact_accepted_p2p: need 1 <= world <= %d, 0 <= rank < world, the peer tables and c, ref, "
@@ -422,7 +423,29 @@ extern "C" int mvs_compact_accepted_p2p(mvs_ctx* ctx, int64_t N, int64_t index_b
         if (!peer_records[d] || !peer_counts[d]) { mvs_set_error("mvs_compact_accepted_p2p: null peer pointer %d", d); return MVS_ERR_ARG; }
     MVS_CUDA_CHECK(cudaSetDevice(ctx->device));
     return mvs_launch_compact_p2p(ctx, N, index_base, c, nrm, ref, vis_mask, avg, count, xy, gate, bound, peer_records,
-                                  peer_counts, rank, world, capacity, (cudaStream_t)stream);
+                                  peer_counts, rank, world, wire, capacity, (cudaStream_t)stream);
+}
+
+extern "C" int mvs_wire_bytes(const mvs_ctx* ctx, int wire) {
+    if (!ctx) return 0;
+    const int mwb = 8 * ((ctx->V + 63) / 64);
+    if (wire == MVS_WIRE_COMPACT) return 56 + mwb;
+    if (wire == MVS_WIRE_FULL) return (int)sizeof(mvs_patch_record) + mwb;
+    return 0;
+}
+
+extern "C" int mvs_records_expand(mvs_ctx* ctx, int wire, const void* wire_records, int64_t n, void* records, void* stream) {
+    if (!ctx) { mvs_set_error("mvs_records_expand: null context"); return MVS_ERR_ARG; }
+    if (n < 0 || (n > 0 && (!wire_records || !records))) { mvs_set_error("mvs_records_expand: null buffer"); return MVS_ERR_ARG; }
+    MVS_CUDA_CHECK(cudaSetDevice(ctx->device));
+    if (wire == MVS_WIRE_FULL) {
+        if (n > 0 && wire_records != records)
+            MVS_CUDA_CHECK(cudaMemcpyAsync(records, wire_records, (size_t)n * mvs_wire_bytes(ctx, wire), cudaMemcpyDeviceToDevice,
+                                           (cudaStream_t)stream));
+        return MVS_OK;
+    }
+    if (wire != MVS_WIRE_COMPACT) { mvs_set_error("mvs_records_expand: unknown wire format %d", wire); return MVS_ERR_ARG; }
+    return mvs_launch_records_expand(ctx, wire_records, n, records, (cudaStream_t)stream);
 }
 
 extern "C" int mvs_score_pmvs(mvs_ctx* ctx, int64_t N, const double* c, const double* nrm, const int32_t* ref,

@@ -79,7 +79,7 @@ def test_fused_compaction_all_gather_layout(golden, built_lib):
         cnts = (C.c_void_p * world)(*[x.data_ptr() for x in counts])
         for rank in range(world):
             assert lib.mvs_compact_accepted_p2p(ctx._h, N, 1000, p(c), p(nrm), p(ref), p(out["vis_mask"]), p(out["avg"]),
-                                                p(out["count"]), p(out["xy"]), None, 2, recs, cnts, rank, world, cap, sp) == 0
+                                                p(out["count"]), p(out["xy"]), None, 2, recs, cnts, rank, world, 0, cap, sp) == 0
         torch.cuda.synchronize()
         k = int(n_want.item())
         assert 0 < k < N
@@ -90,6 +90,48 @@ def test_fused_compaction_all_gather_layout(golden, built_lib):
                 assert not inbox[g][rank * cap + k: (rank + 1) * cap].any()
         # an empty batch publishes a zero count
         assert lib.mvs_compact_accepted_p2p(ctx._h, 0, 0, None, None, None, None, None, None, None, None, 2, recs, cnts, 1,
-                                            world, cap, sp) == 0
+                                            world, 0, cap, sp) == 0
         torch.cuda.synchronize()
         assert counts[0].tolist() == [k, 0] and counts[1].tolist() == [k, 0]
+
+
+def test_compact_wire_records_expand_to_the_same_bytes(golden, built_lib):
+    """MVS_WIRE_COMPACT drops what the receiver can recompute (n, xy, count).  For patches built the way
+    the reference builds every patch -- n = (O_ref - c)/|O_ref - c| (MVS2.py:247, 357-358) -- expanding the
+    compact records on the "receiving GPU" reproduces the full records bit for bit."""
+    import ctypes as C
+    import torch
+    import mvs_b200
+    from mvs_b200 import _lib
+    d = golden("dino12_scores")
+    lib = _lib.load()
+    with mvs_b200.MvsContext(d["rgb"], d["K"], d["R"], d["t"], Rrt=d["Rrt"]) as ctx:
+        rb, wb = lib.mvs_record_bytes(ctx._h), lib.mvs_wire_bytes(ctx._h, 1)
+        assert lib.mvs_wire_bytes(ctx._h, 0) == rb and wb == 56 + 8 and wb < rb
+        _, cen = ctx.cameras()
+        q = cen[d["ref"]] - d["c"]
+        dist = np.sqrt(q[:, 0] * q[:, 0] + q[:, 1] * q[:, 1] + q[:, 2] * q[:, 2])     # left to right, like the device
+        c = torch.from_numpy(d["c"]).cuda()
+        ref = torch.from_numpy(d["ref"]).cuda()
+        nrm = torch.from_numpy(q / dist[:, None]).cuda()
+        out = ctx.score_device(c, ref, min_ncc=0.4)
+        N = c.shape[0]
+        p = lambda x: C.c_void_p(x.data_ptr())
+        sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        full = torch.zeros((N, rb), dtype=torch.uint8, device="cuda")
+        n_full = torch.zeros(1, dtype=torch.int64, device="cuda")
+        assert lib.mvs_compact_accepted(ctx._h, N, 7, p(c), p(nrm), p(ref), p(out["vis_mask"]), p(out["avg"]), p(out["count"]),
+                                        p(out["xy"]), None, 2, p(full), N, p(n_full), sp) == 0
+        wire = torch.zeros((N, wb), dtype=torch.uint8, device="cuda")
+        n_wire = torch.full((1,), -1, dtype=torch.int64, device="cuda")
+        recs = (C.c_void_p * 1)(wire.data_ptr())
+        cnts = (C.c_void_p * 1)(n_wire.data_ptr())
+        assert lib.mvs_compact_accepted_p2p(ctx._h, N, 7, p(c), None, p(ref), p(out["vis_mask"]), p(out["avg"]), p(out["count"]),
+                                            p(out["xy"]), None, 2, recs, cnts, 0, 1, 1, N, sp) == 0
+        torch.cuda.synchronize()
+        k = int(n_full.item())
+        assert k == int(n_wire.item()) and k > 100
+        back = torch.zeros((k, rb), dtype=torch.uint8, device="cuda")
+        assert lib.mvs_records_expand(ctx._h, 1, p(wire), k, p(back), sp) == 0
+        torch.cuda.synchronize()
+        assert torch.equal(back, full[:k])
