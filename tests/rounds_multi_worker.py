@@ -1,0 +1,48 @@
+"""Worker of tests/test_rounds_multi_gpu.py: run under torchrun, one process per GPU.  Every rank runs the
+round driver with the candidates sharded over the ranks (NCCL all-gather of accepted records per round)
+and, in a second context, unsharded; the accepted records and the cell tables must be identical."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    import mvs_b200
+    from mvs_b200 import records
+    from mvs_b200.rounds import DeviceBackend, RoundDriver
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    s = np.load(os.path.join(ROOT, "tests", "golden", "dino12_scores.npz"))
+    e = np.load(os.path.join(ROOT, "tests", "golden", "dino12_expansion.npz"))
+    V = s["rgb"].shape[0]
+    ns = int(e["n_seeds"])
+    seeds = records.make_records(V, e["c"][:ns], e["n"][:ns], e["xy"][:ns], e["avg"][:ns], e["ref"][:ns], e["vis"][:ns])
+    out = {}
+    for name, (r, w) in (("sharded", (rank, world)), ("single", (0, 1))):
+        with mvs_b200.MvsContext(s["rgb"], s["K"], s["R"], s["t"], Rrt=s["Rrt"], device=local) as ctx:
+            be = DeviceBackend(ctx, cell_size=2, scale=float(e["scale"]), bound=int(e["bound"]), table=e["table_before"])
+            drv = RoundDriver(be, rank=r, world=w)
+            acc = drv.run(be.to_device(seeds), max_rounds=6)
+            out[name] = (np.concatenate([be.to_host(a) for a in acc]) if acc else None, be.table(), drv.stats)
+    a, b = out["sharded"], out["single"]
+    same = (a[0] is not None and b[0] is not None and a[0].tobytes() == b[0].tobytes() and np.array_equal(a[1], b[1]))
+    shards = [st["shard"] for st in a[2]]
+    ok = torch.tensor([int(same and len(a[0]) > 50)], device="cuda")
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("ROUNDS_MULTI", "OK" if ok.item() else "MISMATCH", "world", world, "patches", len(a[0]), "rounds", len(a[2]),
+              "shards", shards[:3], flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    return 0 if ok.item() else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())
