@@ -68,9 +68,13 @@ struct mvs_ctx {
     // Mode B texture path (ncc_pmvs.cu), created on the first Mode B call
     int pmvs_ready;
     int64_t pmvs_serial;
-    cudaArray_t* pmvs_arrays;              // [V] host table of 2-D gather-enabled arrays
-    cudaTextureObject_t* pmvs_tex_host;    // [V]
+    int pmvs_n_atlas;
+    cudaArray_t* pmvs_arrays;              // [n_atlas] gather-enabled 2-D arrays, views tiled inside
+    cudaTextureObject_t* pmvs_atlas_tex;   // [n_atlas]
+    cudaTextureObject_t* pmvs_tex_host;    // [V] the atlas handle of each view
+    float* pmvs_off_host;                  // [V,2] tile origin of each view
     void* d_pmvs_tex;                      // [V] cudaTextureObject_t
+    void* d_pmvs_off;                      // [V] float2
     void* d_pmvs_camf;                     // [V] CamProjF
     CamProj* d_cam;       // [V]
     CamGeom* d_geom;      // [V]

@@ -41,11 +41,13 @@ struct __align__(16) CamProjF {
 // per device; re-uploaded when another context scored last (mvs_launch_score_pmvs).
 #define PMVS_MAX_VIEWS 1024
 __constant__ cudaTextureObject_t c_tex[PMVS_MAX_VIEWS];
+__constant__ float2 c_off[PMVS_MAX_VIEWS];         // tile origin of each view inside its atlas
 
 struct PmvsArgs {
     const CamProj* cams;
     const CamProjF* camsf;
     const cudaTextureObject_t* tex;
+    const float2* off;         // [V] tile origin of each view inside its atlas
     int V, H, W;
     int flags;
     int group;                 // hypotheses per selection set (<= 1: no selection)
@@ -125,13 +127,15 @@ struct __align__(16) ViewAffine {
 // Bilinear sample through the gather path.  (u0, v0) = integer tap origin (pixel centres at
 // integers), (fu, fv) = fractions.  Returns the value in [0,1] and whether all four taps are
 // inside the image.
-__device__ __forceinline__ float tap4(cudaTextureObject_t tex, float u0, float v0, float fu, float fv, bool front,
+__device__ __forceinline__ float tap4(cudaTextureObject_t tex, float2 off, float u0, float v0, float fu, float fv, bool front,
                                       float wm2, float hm2, bool& ok) {
-    ok = front && (u0 >= 0.0f) && (u0 <= wm2) && (v0 >= 0.0f) && (v0 <= hm2);
+    ok = front && (u0 >= 0.0f) && (u0 <= wm2) && (v0 >= 0.0f) && (v0 <= hm2);       // inside the VIEW, not the atlas
+    u0 += off.x;
+    v0 += off.y;
     // the footprint of a gather at (u0+1, v0+1) is texels (u0..u0+1, v0..v0+1); the centre of
     // the 2x2 block is the robust coordinate.  Components: x=(0,1) y=(1,1) z=(1,0) w=(0,0) as
     // (column offset, row offset).
-    const float4 g = tex2Dgather<float4>(tex, ok ? u0 + 1.0f : 1.0f, ok ? v0 + 1.0f : 1.0f, 0);
+    const float4 g = tex2Dgather<float4>(tex, ok ? u0 + 1.0f : off.x + 1.0f, ok ? v0 + 1.0f : off.y + 1.0f, 0);
     const float top = fmaf(fu, g.z - g.w, g.w);
     const float bot = fmaf(fu, g.y - g.x, g.x);
     return fmaf(fv, bot - top, top);
@@ -147,6 +151,8 @@ __global__ void __launch_bounds__(32, MINB) ncc_score_pmvs(const PmvsArgs A, int
     // in a uniform register (no per-lane waterfall loop around TLD4) and keeps the gathers of a
     // batch of views in flight together.
     __shared__ ViewAffine s_view[1][33];                   // 32 views of the current block + the reference view
+    __shared__ float s_val[16][MU * MU];                   // samples of 16 views (row stride MU^2 is odd: no bank conflicts)
+    __shared__ float s_dref[MU * MU];                      // pivot-shifted samples of the reference view
 
     const int lane = threadIdx.x;
     constexpr int wib = 0;
@@ -250,7 +256,7 @@ __global__ void __launch_bounds__(32, MINB) ncc_score_pmvs(const PmvsArgs A, int
 
             // Issue the taps of the view staged in `slot` (no warp-synchronous operation in here,
             // so the gathers of a whole batch of views are in flight together).
-            auto issue_view = [&](int slot, cudaTextureObject_t tex, float (&val)[SPL], bool& ok_all) {
+            auto issue_view = [&](int slot, cudaTextureObject_t tex, float2 off, float (&val)[SPL], bool& ok_all) {
                 const float4* pv = reinterpret_cast<const float4*>(&s_view[wib][slot]);
                 const float4 q0 = pv[0], q1 = pv[1], q2 = pv[2];          // iu fu iv fv | Z0 hxZ hyZ gxu | gyu gxv gyv -
                 ok_all = true;
@@ -275,14 +281,13 @@ __global__ void __launch_bounds__(32, MINB) ncc_score_pmvs(const PmvsArgs A, int
                         front = z > 0.0f;
                     }
                     bool ok;
-                    val[q] = tap4(tex, u0, v0, fu, fv, front, wm2, hm2, ok);
+                    val[q] = tap4(tex, off, u0, v0, fu, fv, front, wm2, hm2, ok);
                     ok_all &= ok || !live[q];
                 }
             };
 
             double acc = 0.0;
             int count = 0;
-            float dref[SPL];
             float Sr = 0.0f, ssr = 0.0f;
             for (int w32 = 0; w32 < 2 * mw; ++w32) {       // 32 views per mask word
                 uint32_t word = 0u;
@@ -296,15 +301,16 @@ __global__ void __launch_bounds__(32, MINB) ncc_score_pmvs(const PmvsArgs A, int
                         // ---- the reference view's own samples
                         bool ok_all;
                         float val[SPL];
-                        issue_view(r < 32 ? r : 32, A.tex[r], val, ok_all);
+                        issue_view(r < 32 ? r : 32, A.tex[r], A.off[r], val, ok_all);
                         hyp_ok = __all_sync(FULL, ok_all);
                         const float pivot = __shfl_sync(FULL, val[0], 0);
                         float s = 0.0f, ss = 0.0f;
 #pragma unroll
                         for (int q = 0; q < SPL; ++q) {
-                            dref[q] = live[q] ? val[q] - pivot : 0.0f;
-                            s += dref[q];
-                            ss = fmaf(dref[q], dref[q], ss);
+                            const float dq = live[q] ? val[q] - pivot : 0.0f;
+                            if (live[q]) s_dref[lane + 32 * q] = dq;
+                            s += dq;
+                            ss = fmaf(dq, dq, ss);
                         }
                         Sr = warp_sum(s);
                         ssr = warp_sum(ss) - Sr * Sr * (1.0f / NS);  // sum of squared deviations of the reference samples
@@ -317,48 +323,63 @@ __global__ void __launch_bounds__(32, MINB) ncc_score_pmvs(const PmvsArgs A, int
                     for (int half = 0; half < 2; ++half) {
                         const int vbase = w32 * 32 + half * 16;
                         if (vbase >= A.V) break;
-                        float pa[16], pb[16], pc[16];
-                        uint32_t usable16 = 0u;
-                        constexpr int TB = SPL == 1 ? 16 : (SPL == 2 ? 8 : 4);   // views whose gathers fly together
+                        // ---- phase 1: lanes span the samples.  Taps of TB views are issued together, the
+                        // interpolated values go to shared memory [view][sample].
+                        constexpr int TB = SPL == 1 ? 16 : (SPL == 2 ? 8 : 4);
+                        uint32_t bad = 0u;                                   // bit j: some tap of view j is outside
+                        __syncwarp();                                        // the previous half's readers are done
 #pragma unroll
                         for (int j0 = 0; j0 < 16; j0 += TB) {
                             float val[TB][SPL];
                             bool okl[TB];
 #pragma unroll
-                            for (int jj = 0; jj < TB; ++jj) {
+                            for (int jj = 0; jj < TB; ++jj)
                                 // views past the last one re-sample it (branch-free); their sums are never scored
-                                issue_view(half * 16 + j0 + jj, c_tex[min(vbase + j0 + jj, A.V - 1)], val[jj], okl[jj]);
-                            }
+                                issue_view(half * 16 + j0 + jj, c_tex[min(vbase + j0 + jj, A.V - 1)], c_off[min(vbase + j0 + jj, A.V - 1)], val[jj], okl[jj]);
 #pragma unroll
                             for (int jj = 0; jj < TB; ++jj) {
-                                const int j = j0 + jj;
-                                if (__all_sync(FULL, okl[jj])) usable16 |= 1u << j;
-                                const float pivot = __shfl_sync(FULL, val[jj][0], 0);
-                                pa[j] = pb[j] = pc[j] = 0.0f;
+                                if (!okl[jj]) bad |= 1u << (j0 + jj);
 #pragma unroll
-                                for (int q = 0; q < SPL; ++q) {
-                                    const float d = live[q] ? val[jj][q] - pivot : 0.0f;
-                                    pa[j] += d;
-                                    pb[j] = fmaf(d, d, pb[j]);
-                                    pc[j] = fmaf(d, dref[q], pc[j]);
-                                }
+                                for (int q = 0; q < SPL; ++q)
+                                    if (live[q]) s_val[j0 + jj][lane + 32 * q] = val[jj][q];
                             }
                         }
-                        const float Sd = butterfly16f(pa, lane);
-                        const float SSd = butterfly16f(pb, lane);
-                        const float SAB = butterfly16f(pc, lane);
-                        const int vj = lane_view16(lane);
+                        const uint32_t usable16 = ~__reduce_or_sync(FULL, bad);
+                        __syncwarp();
+                        // ---- phase 2: lanes span the VIEWS.  Lane L sums half of the samples of view L & 15
+                        // (pivot = the view's first sample, so low-variance windows keep full fp32 precision);
+                        // one shuffle per quantity joins the halves -- no butterfly.
+                        constexpr int NH = (NS + 1) / 2;
+                        const int vj = lane & 15;
+                        const float* row = s_val[vj];
+                        const float pivot = row[0];
+                        const int m0 = (lane & 16) ? NH : 0;
+                        const int m1 = (lane & 16) ? NS : NH;
+                        float Sd = 0.0f, SSd = 0.0f, SAB = 0.0f;
+#pragma unroll
+                        for (int t = 0; t < NH; ++t) {
+                            const int m = m0 + t;
+                            if (m < m1) {
+                                const float dd = row[m] - pivot;
+                                Sd += dd;
+                                SSd = fmaf(dd, dd, SSd);
+                                SAB = fmaf(dd, s_dref[m], SAB);
+                            }
+                        }
+                        Sd += __shfl_xor_sync(FULL, Sd, 16);
+                        SSd += __shfl_xor_sync(FULL, SSd, 16);
+                        SAB += __shfl_xor_sync(FULL, SAB, 16);
                         const int v = vbase + vj;
                         const float ss = SSd - Sd * Sd * (1.0f / NS);
                         const float cov = SAB - Sd * Sr * (1.0f / NS);
                         const bool scored = (v < A.V) && (v != r) && ((usable16 >> vj) & 1u) &&
                                             ((cand32 >> (half * 16 + vj)) & 1u) && (ss * (1.0f / NS) >= PMVS_VAR_MIN) &&
                                             (ssr * (1.0f / NS) >= PMVS_VAR_MIN);
-                        const float val = cov * rsqrtf(ss * ssr) * cn;
-                        const bool vis = scored && (val > A.thr) && !(lane & 1);   // each view is held by a lane pair
-                        if (vis) acc += (double)val;
-                        word |= __reduce_or_sync(FULL, vis ? (1u << (half * 16 + vj)) : 0u);
-                        if (A.ncc_out && v < A.V && !(lane & 1)) A.ncc_out[h * A.V + v] = scored ? val : nanf("");
+                        const float val_ncc = cov * rsqrtf(ss * ssr) * cn;
+                        const bool vis = scored && (val_ncc > A.thr) && (lane < 16);   // lanes 16..31 hold duplicates
+                        if (vis) acc += (double)val_ncc;
+                        word |= __ballot_sync(FULL, vis) << (half * 16);
+                        if (A.ncc_out && v < A.V && lane < 16) A.ncc_out[h * A.V + v] = scored ? val_ncc : nanf("");
                     }
                 } else if (A.ncc_out) {
                     for (int v = w32 * 32 + lane; v < min(A.V, w32 * 32 + 32); v += 32) A.ncc_out[h * A.V + v] = nanf("");
@@ -421,8 +442,12 @@ int mvs_launch_select_best(mvs_ctx* ctx, int64_t N, int group, const double* avg
 }
 
 // ---------------------------------------------------------------------------------
-// Texture path set-up (once per context, on the first Mode B call): one 2-D gather-enabled
-// CUDA array per view holding its gray image, a table of texture objects, fp32 cameras.
+// Texture path set-up (once per context, on the first Mode B call): the gray images of all views
+// are tiled into as few gather-enabled 2-D CUDA arrays ("atlases") as the device's texture size
+// limit allows -- ONE for every BASELINE shape up to 128 x 1080p, three for 256 x 4K.  One
+// texture object per view was measured 1.6x slower: every TLD4 of a warp then names a different
+// texture header (47 views x 16 warps per SM) and the header cache thrashes.  A view is addressed
+// by its tile offset; taps are validated against the view's own bounds, so tiles never bleed.
 // ---------------------------------------------------------------------------------
 int mvs_pmvs_prepare(mvs_ctx* ctx, cudaStream_t s) {
     if (ctx->pmvs_ready) return MVS_OK;
@@ -432,11 +457,31 @@ int mvs_pmvs_prepare(mvs_ctx* ctx, cudaStream_t s) {
     CamProj* hp = nullptr;
     CamProjF* hf = nullptr;
     cudaTextureObject_t* htex = nullptr;
-    ctx->pmvs_arrays = (cudaArray_t*)calloc(V, sizeof(cudaArray_t));
+    int max_w = 0, max_h = 0;
+    if (cudaDeviceGetAttribute(&max_w, cudaDevAttrMaxTexture2DGatherWidth, ctx->device) != cudaSuccess ||
+        cudaDeviceGetAttribute(&max_h, cudaDevAttrMaxTexture2DGatherHeight, ctx->device) != cudaSuccess || max_w < W ||
+        max_h < H) {
+        cudaGetLastError();
+        mvs_set_error("Mode B set-up: a %d x %d view does not fit a gather texture (limit %d x %d)", W, H, max_w, max_h);
+        return MVS_ERR_ARG;
+    }
+    const int fit_x = max_w / W, fit_y = max_h / H;
+    const int tiles_x = V < fit_x ? V : fit_x;                         // tiles per atlas row
+    const int rows_all = (V + tiles_x - 1) / tiles_x;                  // tile rows needed in total
+    const int rows_per = rows_all < fit_y ? rows_all : fit_y;          // tile rows per atlas
+    const int per_atlas = tiles_x * rows_per;
+    const int n_atlas = (V + per_atlas - 1) / per_atlas;
+    ctx->pmvs_n_atlas = n_atlas;
+    ctx->pmvs_arrays = (cudaArray_t*)calloc(n_atlas, sizeof(cudaArray_t));
+    ctx->pmvs_atlas_tex = (cudaTextureObject_t*)calloc(n_atlas, sizeof(cudaTextureObject_t));
     ctx->pmvs_tex_host = (cudaTextureObject_t*)calloc(V, sizeof(cudaTextureObject_t));
+    ctx->pmvs_off_host = (float*)calloc(2 * (size_t)V, sizeof(float));
     hp = (CamProj*)malloc(sizeof(CamProj) * V);
     hf = (CamProjF*)calloc(V, sizeof(CamProjF));
-    if (!ctx->pmvs_arrays || !ctx->pmvs_tex_host || !hp || !hf) { rc = MVS_ERR_NOMEM; goto done; }
+    if (!ctx->pmvs_arrays || !ctx->pmvs_atlas_tex || !ctx->pmvs_tex_host || !ctx->pmvs_off_host || !hp || !hf) {
+        rc = MVS_ERR_NOMEM;
+        goto done;
+    }
     htex = ctx->pmvs_tex_host;
     if (cudaMalloc(&d_planar, (size_t)V * H * W) != cudaSuccess) {
         cudaGetLastError();
@@ -447,33 +492,42 @@ int mvs_pmvs_prepare(mvs_ctx* ctx, cudaStream_t s) {
     if ((rc = mvs_launch_unpack_gray(ctx, d_planar, s)) != MVS_OK) goto done;
     {
         cudaChannelFormatDesc fmt = cudaCreateChannelDesc<unsigned char>();
-        for (int v = 0; v < V; ++v) {
-            if (cudaMallocArray(&ctx->pmvs_arrays[v], &fmt, W, H, cudaArrayTextureGather) != cudaSuccess) {
-                mvs_set_error("Mode B set-up: cudaMallocArray (%d x %d, view %d) failed: %s", W, H, v,
+        for (int a = 0; a < n_atlas; ++a) {
+            const int v_lo = a * per_atlas, v_hi = (v_lo + per_atlas < V) ? v_lo + per_atlas : V;
+            const int rows = (v_hi - v_lo + tiles_x - 1) / tiles_x;
+            if (cudaMallocArray(&ctx->pmvs_arrays[a], &fmt, (size_t)tiles_x * W, (size_t)rows * H, cudaArrayTextureGather) !=
+                cudaSuccess) {
+                mvs_set_error("Mode B set-up: cudaMallocArray (%d x %d atlas) failed: %s", tiles_x * W, rows * H,
                               cudaGetErrorString(cudaGetLastError()));
                 rc = MVS_ERR_NOMEM;
-                goto done;
-            }
-            if (cudaMemcpy2DToArrayAsync(ctx->pmvs_arrays[v], 0, 0, d_planar + (size_t)v * H * W, W, W, H,
-                                         cudaMemcpyDeviceToDevice, s) != cudaSuccess) {
-                mvs_set_error("Mode B set-up: copy to array failed: %s", cudaGetErrorString(cudaGetLastError()));
-                rc = MVS_ERR_CUDA;
                 goto done;
             }
             cudaResourceDesc rd;
             memset(&rd, 0, sizeof(rd));
             rd.resType = cudaResourceTypeArray;
-            rd.res.array.array = ctx->pmvs_arrays[v];
+            rd.res.array.array = ctx->pmvs_arrays[a];
             cudaTextureDesc td;
             memset(&td, 0, sizeof(td));
             td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
             td.filterMode = cudaFilterModePoint;
             td.readMode = cudaReadModeNormalizedFloat;
             td.normalizedCoords = 0;
-            if (cudaCreateTextureObject(&htex[v], &rd, &td, nullptr) != cudaSuccess) {
+            if (cudaCreateTextureObject(&ctx->pmvs_atlas_tex[a], &rd, &td, nullptr) != cudaSuccess) {
                 mvs_set_error("Mode B set-up: cudaCreateTextureObject failed: %s", cudaGetErrorString(cudaGetLastError()));
                 rc = MVS_ERR_CUDA;
                 goto done;
+            }
+            for (int v = v_lo; v < v_hi; ++v) {
+                const int tx = (v - v_lo) % tiles_x, ty = (v - v_lo) / tiles_x;
+                if (cudaMemcpy2DToArrayAsync(ctx->pmvs_arrays[a], (size_t)tx * W, (size_t)ty * H, d_planar + (size_t)v * H * W, W, W,
+                                             H, cudaMemcpyDeviceToDevice, s) != cudaSuccess) {
+                    mvs_set_error("Mode B set-up: copy to atlas failed: %s", cudaGetErrorString(cudaGetLastError()));
+                    rc = MVS_ERR_CUDA;
+                    goto done;
+                }
+                htex[v] = ctx->pmvs_atlas_tex[a];
+                ctx->pmvs_off_host[2 * v] = (float)(tx * W);
+                ctx->pmvs_off_host[2 * v + 1] = (float)(ty * H);
             }
         }
     }
@@ -482,13 +536,15 @@ int mvs_pmvs_prepare(mvs_ctx* ctx, cudaStream_t s) {
         for (int i = 0; i < 9; ++i) hf[v].r[i] = (float)hp[v].r[i];
         hf[v].fx = (float)hp[v].fx; hf[v].fy = (float)hp[v].fy; hf[v].cx = (float)hp[v].cx; hf[v].cy = (float)hp[v].cy;
     }
-    if (cudaMalloc(&ctx->d_pmvs_tex, sizeof(cudaTextureObject_t) * V) != cudaSuccess ||
+    if (cudaMalloc(&ctx->d_pmvs_off, sizeof(float) * 2 * V) != cudaSuccess ||
+        cudaMalloc(&ctx->d_pmvs_tex, sizeof(cudaTextureObject_t) * V) != cudaSuccess ||
         cudaMalloc(&ctx->d_pmvs_camf, sizeof(CamProjF) * V) != cudaSuccess) {
         cudaGetLastError();
         rc = MVS_ERR_NOMEM;
         goto done;
     }
-    if (cudaMemcpyAsync(ctx->d_pmvs_tex, htex, sizeof(cudaTextureObject_t) * V, cudaMemcpyHostToDevice, s) != cudaSuccess ||
+    if (cudaMemcpyAsync(ctx->d_pmvs_off, ctx->pmvs_off_host, sizeof(float) * 2 * V, cudaMemcpyHostToDevice, s) != cudaSuccess ||
+        cudaMemcpyAsync(ctx->d_pmvs_tex, htex, sizeof(cudaTextureObject_t) * V, cudaMemcpyHostToDevice, s) != cudaSuccess ||
         cudaMemcpyAsync(ctx->d_pmvs_camf, hf, sizeof(CamProjF) * V, cudaMemcpyHostToDevice, s) != cudaSuccess ||
         cudaStreamSynchronize(s) != cudaSuccess) {
         mvs_set_error("Mode B set-up: upload failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -508,18 +564,25 @@ done:
 }
 
 void mvs_pmvs_release(mvs_ctx* ctx) {
-    if (ctx->pmvs_tex_host) {
-        for (int v = 0; v < ctx->V; ++v)
-            if (ctx->pmvs_tex_host[v]) cudaDestroyTextureObject(ctx->pmvs_tex_host[v]);
-        free(ctx->pmvs_tex_host);
-        ctx->pmvs_tex_host = nullptr;
+    if (ctx->pmvs_atlas_tex) {
+        for (int a = 0; a < ctx->pmvs_n_atlas; ++a)
+            if (ctx->pmvs_atlas_tex[a]) cudaDestroyTextureObject(ctx->pmvs_atlas_tex[a]);
+        free(ctx->pmvs_atlas_tex);
+        ctx->pmvs_atlas_tex = nullptr;
     }
     if (ctx->pmvs_arrays) {
-        for (int v = 0; v < ctx->V; ++v)
-            if (ctx->pmvs_arrays[v]) cudaFreeArray(ctx->pmvs_arrays[v]);
+        for (int a = 0; a < ctx->pmvs_n_atlas; ++a)
+            if (ctx->pmvs_arrays[a]) cudaFreeArray(ctx->pmvs_arrays[a]);
         free(ctx->pmvs_arrays);
         ctx->pmvs_arrays = nullptr;
     }
+    free(ctx->pmvs_tex_host);
+    ctx->pmvs_tex_host = nullptr;
+    free(ctx->pmvs_off_host);
+    ctx->pmvs_off_host = nullptr;
+    ctx->pmvs_n_atlas = 0;
+    if (ctx->d_pmvs_off) cudaFree(ctx->d_pmvs_off);
+    ctx->d_pmvs_off = nullptr;
     if (ctx->d_pmvs_tex) cudaFree(ctx->d_pmvs_tex);
     if (ctx->d_pmvs_camf) cudaFree(ctx->d_pmvs_camf);
     ctx->d_pmvs_tex = nullptr;
@@ -540,6 +603,7 @@ int mvs_launch_score_pmvs(mvs_ctx* ctx, int64_t N, const double* c, const double
     if (ctx->device < 64 && (table_owner[ctx->device] != ctx || table_serial[ctx->device] != ctx->pmvs_serial)) {
         MVS_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_tex, ctx->pmvs_tex_host, sizeof(cudaTextureObject_t) * ctx->V, 0,
                                                cudaMemcpyHostToDevice, s));
+        MVS_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_off, ctx->pmvs_off_host, sizeof(float) * 2 * ctx->V, 0, cudaMemcpyHostToDevice, s));
         table_owner[ctx->device] = ctx;
         table_serial[ctx->device] = ctx->pmvs_serial;
     }
@@ -547,6 +611,7 @@ int mvs_launch_score_pmvs(mvs_ctx* ctx, int64_t N, const double* c, const double
     A.cams = ctx->d_cam;
     A.camsf = (const CamProjF*)ctx->d_pmvs_camf;
     A.tex = (const cudaTextureObject_t*)ctx->d_pmvs_tex;
+    A.off = (const float2*)ctx->d_pmvs_off;
     A.V = ctx->V; A.H = ctx->H; A.W = ctx->W;
     A.flags = flags; A.group = group; A.bound = bound; A.thr = (float)thr;
     A.c = c; A.nrm = nrm; A.ref = ref; A.cand = cand;
