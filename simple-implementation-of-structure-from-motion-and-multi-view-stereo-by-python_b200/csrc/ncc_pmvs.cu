@@ -151,7 +151,10 @@ __global__ void __launch_bounds__(32, MINB) ncc_score_pmvs(const PmvsArgs A, int
     // in a uniform register (no per-lane waterfall loop around TLD4) and keeps the gathers of a
     // batch of views in flight together.
     __shared__ ViewAffine s_view[1][33];                   // 32 views of the current block + the reference view
-    __shared__ float s_val[16][MU * MU];                   // samples of 16 views (row stride MU^2 is odd: no bank conflicts)
+    // samples of 16 views.  Row stride = 2 (mod 32) and the second half-warp starts at an odd sample
+    // offset, so the 32 lanes of phase 2 (16 views x 2 sample halves) hit 32 different banks.
+    constexpr int VSTRIDE = ((MU * MU + 29) / 32) * 32 + 2;
+    __shared__ float s_val[16][VSTRIDE];
     __shared__ float s_dref[MU * MU];                      // pivot-shifted samples of the reference view
 
     const int lane = threadIdx.x;
