@@ -66,6 +66,20 @@ def test_pmvs_matches_spec(built_lib, mu):
     assert np.array_equal(out["xy"][seen, 0], want["x"][seen])  # centre projection: same fp64 path as Mode A
 
 
+@pytest.mark.parametrize("V,mu", [(47, 5), (70, 5), (40, 7)])
+def test_pmvs_many_views(built_lib, V, mu):
+    """47 views is the shape of BASELINE config 3 (two blocks of 32 views, reference views >= 32 take the
+    extra staging slot); 70 views needs two mask words and three blocks."""
+    import mvs_b200
+    from oracle import mode_b
+    rgb, K, R, t, cams, gray, c, nrm, ref = _ring(V=V, H=240, W=320, n=1500, seed=7)
+    want = mode_b.score(gray, cams, c, nrm, ref, 0.7, mu=mu)
+    with mvs_b200.MvsContext(rgb, K, R, t, Rrt=cams.R) as ctx:
+        out = ctx.score_pmvs_host(c, nrm, ref, min_ncc=0.7, mu=mu, want_ncc=True)
+    _check_against(out, want, V, 0.7)
+    assert (ref >= 32).any() and want["count"][ref >= 32].max() >= 2
+
+
 def test_pmvs_candidate_mask(built_lib):
     import mvs_b200
     from oracle import mode_b
