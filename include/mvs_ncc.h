@@ -260,6 +260,16 @@ int mvs_round_score(mvs_ctx* ctx, const void* frontier, int64_t begin, int64_t e
                     double scale, void* records, int64_t capacity, int64_t* n_out, void* stream);
 
 /*
+ * Phase 2 with the exchange fused in (see mvs_compact_accepted_p2p): the passing records of this
+ * GPU's shard are stored, in slot order, into region `rank` of EVERY GPU's inbox and their number
+ * into slot `rank` of every count array; an empty shard publishes a zero count.  `capacity` (records
+ * per region) must be >= end - begin.  Replaces: mvs_round_score + the all-gather of the records.
+ */
+int mvs_round_score_p2p(mvs_ctx* ctx, const void* frontier, int64_t begin, int64_t end, double min_ncc, int wid, int bound,
+                        double scale, void* const* peer_records, int64_t* const* peer_counts, int rank, int world,
+                        int wire, int64_t capacity, void* stream);
+
+/*
  * Phase 3 (identical on every GPU, on the gathered records of ALL shards in ascending
  * slot order): drop a dj=+1 record whose dj=-1 sibling (slot-1) also passed -- the
  * `break` of MVS2.py:404 --, fill the cells of the kept ones (MVS2.py:401-402) and

@@ -276,7 +276,9 @@ def patch_expansion(args, imgs, initial_patches, cells, camera_pos, visible_lowe
             rank, world = dist.get_rank(), dist.get_world_size()
     except ImportError:
         pass
-    drv = RoundDriver(be, rank=rank, world=world, group=group, timing=bool(os.environ.get("MVS_TIME_ROUNDS")))
+    # multi-GPU exchange: fused into the compaction over NVLink P2P stores unless MVS_EXCHANGE=collective
+    drv = RoundDriver(be, rank=rank, world=world, group=group, timing=bool(os.environ.get("MVS_TIME_ROUNDS")),
+                      exchange=os.environ.get("MVS_EXCHANGE", "p2p"))
     max_rounds = int(os.environ.get("MVS_MAX_ROUNDS", "100000"))
     max_iter = int(os.environ.get("MVS_MAX_ITERATIONS", "100000"))        # the reference's cap: iteration < 100000 (MVS2.py:321)
     max_patches = os.environ.get("MVS_MAX_PATCHES")

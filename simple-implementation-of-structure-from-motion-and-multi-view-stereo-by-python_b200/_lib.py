@@ -37,6 +37,8 @@ SYMBOLS = {
     "mvs_round_generate": (C.c_int, [_P, _P, C.c_int64, C.POINTER(C.c_int64), _P]),
     "mvs_round_score": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_double, C.c_int, C.c_int, C.c_double, _P, C.c_int64,
                                   _P, _P]),
+    "mvs_round_score_p2p": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_double, C.c_int, C.c_int, C.c_double, _P, _P, C.c_int,
+                                      C.c_int, C.c_int, C.c_int64, _P]),
     "mvs_round_commit": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P]),
     "mvs_round_candidates": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "mvs_ncc_pairs": (C.c_int, [C.c_int, C.c_int64, C.c_int, _P, _P, _P, C.c_int, _P]),

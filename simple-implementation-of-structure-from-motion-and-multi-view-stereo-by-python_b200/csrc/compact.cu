@@ -221,7 +221,8 @@ int mvs_launch_compact(mvs_ctx* ctx, int64_t N, int64_t index_base, const double
 int mvs_launch_compact_p2p(mvs_ctx* ctx, int64_t N, int64_t index_base, const double* c, const double* nrm,
                            const int32_t* ref, const uint64_t* vis, const double* avg, const int32_t* count,
                            const double* xy, const uint8_t* gate, int bound, void* const* peer_records,
-                           int64_t* const* peer_counts, int rank, int world, int wire, int64_t capacity, cudaStream_t s) {
+                           int64_t* const* peer_counts, int rank, int world, int wire, int64_t capacity,
+                           const int64_t* index_arr, const int32_t* px, cudaStream_t s) {
     PeerList P;
     memset(&P, 0, sizeof(P));
     P.world = world;
@@ -231,8 +232,8 @@ int mvs_launch_compact_p2p(mvs_ctx* ctx, int64_t N, int64_t index_base, const do
         P.rec[d] = (uint8_t*)peer_records[d];
         P.cnt[d] = peer_counts[d];
     }
-    return launch_compact_peers(ctx, N, index_base, c, nrm, ref, vis, avg, count, xy, gate, bound, P, capacity, nullptr,
-                                nullptr, s);
+    return launch_compact_peers(ctx, N, index_base, c, nrm, ref, vis, avg, count, xy, gate, bound, P, capacity, index_arr,
+                                px, s);
 }
 
 // ---------------------------------------------------------------------------------

@@ -312,6 +312,24 @@ extern "C" int mvs_round_generate(mvs_ctx* ctx, const void* frontier, int64_t F,
     return MVS_OK;
 }
 
+// shared body of mvs_round_score / mvs_round_score_p2p: score the shard and evaluate the gate
+static int round_score_shard(mvs_ctx* ctx, const void* frontier, int64_t begin, int64_t end, double min_ncc, int wid,
+                             double scale, cudaStream_t s) {
+    const int64_t n = end - begin;
+    if (n == 0) return MVS_OK;
+    const size_t mw = (size_t)((ctx->V + 63) / 64);
+    int rc = mvs_launch_score_refexact(ctx, n, ctx->cand_c + 3 * begin, ctx->cand_ref + begin, min_ncc, wid,
+                                       ctx->cand_vis + mw * begin, ctx->cand_avg + begin, ctx->cand_count + begin,
+                                       ctx->cand_xy + 2 * begin, nullptr, s);
+    if (rc != MVS_OK) return rc;
+    expand_gate<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((const uint8_t*)frontier, rec_bytes_of(ctx), begin, end,
+                                                           ctx->cand_parent, ctx->cand_c, ctx->cand_n, 0.05 / scale,
+                                                           ctx->cand_gate);
+    ctx->launches++;
+    MVS_CUDA_CHECK(cudaGetLastError());
+    return MVS_OK;
+}
+
 extern "C" int mvs_round_score(mvs_ctx* ctx, const void* frontier, int64_t begin, int64_t end, double min_ncc, int wid,
                                int bound, double scale, void* records, int64_t capacity, int64_t* n_out, void* stream) {
     if (!ctx || !ctx->d_cells) { mvs_set_error("mvs_round_score: cell table not initialised"); return MVS_ERR_STATE; }
@@ -328,19 +346,37 @@ extern "C" int mvs_round_score(mvs_ctx* ctx, const void* frontier, int64_t begin
         return MVS_OK;
     }
     const size_t mw = (size_t)((ctx->V + 63) / 64);
-    int rc = mvs_launch_score_refexact(ctx, n, ctx->cand_c + 3 * begin, ctx->cand_ref + begin, min_ncc, wid,
-                                       ctx->cand_vis + mw * begin, ctx->cand_avg + begin, ctx->cand_count + begin,
-                                       ctx->cand_xy + 2 * begin, nullptr, s);
+    int rc = round_score_shard(ctx, frontier, begin, end, min_ncc, wid, scale, s);
     if (rc != MVS_OK) return rc;
-    expand_gate<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((const uint8_t*)frontier, rec_bytes_of(ctx), begin, end,
-                                                           ctx->cand_parent, ctx->cand_c, ctx->cand_n, 0.05 / scale,
-                                                           ctx->cand_gate);
-    ctx->launches++;
-    MVS_CUDA_CHECK(cudaGetLastError());
     return mvs_launch_compact(ctx, n, 0, ctx->cand_c + 3 * begin, ctx->cand_n + 3 * begin, ctx->cand_ref + begin,
                               ctx->cand_vis + mw * begin, ctx->cand_avg + begin, ctx->cand_count + begin,
                               ctx->cand_xy + 2 * begin, ctx->cand_gate + begin, bound, records, capacity, n_out,
                               ctx->cand_slot + begin, ctx->cand_px + 2 * begin, s);
+}
+
+// Phase 2 with the exchange fused in: the passing records of this shard are stored straight into every
+// GPU's inbox (mvs_compact_accepted_p2p semantics, index = slot id), an empty shard publishes a zero count.
+extern "C" int mvs_round_score_p2p(mvs_ctx* ctx, const void* frontier, int64_t begin, int64_t end, double min_ncc, int wid,
+                                   int bound, double scale, void* const* peer_records, int64_t* const* peer_counts,
+                                   int rank, int world, int wire, int64_t capacity, void* stream) {
+    if (!ctx || !ctx->d_cells) { mvs_set_error("mvs_round_score_p2p: cell table not initialised"); return MVS_ERR_STATE; }
+    if (begin < 0 || end < begin || end > ctx->n_cand || capacity < end - begin || !peer_records || !peer_counts ||
+        world < 1 || world > MVS_MAX_PEERS || rank < 0 || rank >= world || (end > begin && !frontier) ||
+        (wire != MVS_WIRE_FULL && wire != MVS_WIRE_COMPACT)) {
+        mvs_set_error("mvs_round_score_p2p: bad shard [%lld, %lld) of %lld candidates, capacity %lld, rank %d of %d",
+                      (long long)begin, (long long)end, (long long)ctx->n_cand, (long long)capacity, rank, world);
+        return MVS_ERR_ARG;
+    }
+    MVS_CUDA_CHECK(cudaSetDevice(ctx->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t n = end - begin;
+    const size_t mw = (size_t)((ctx->V + 63) / 64);
+    int rc = round_score_shard(ctx, frontier, begin, end, min_ncc, wid, scale, s);
+    if (rc != MVS_OK) return rc;
+    return mvs_launch_compact_p2p(ctx, n, 0, ctx->cand_c + 3 * begin, ctx->cand_n + 3 * begin, ctx->cand_ref + begin,
+                                  ctx->cand_vis + mw * begin, ctx->cand_avg + begin, ctx->cand_count + begin,
+                                  ctx->cand_xy + 2 * begin, ctx->cand_gate + begin, bound, peer_records, peer_counts, rank,
+                                  world, wire, capacity, ctx->cand_slot + begin, ctx->cand_px + 2 * begin, s);
 }
 
 extern "C" int mvs_round_commit(mvs_ctx* ctx, const void* records, int64_t n, void* next_frontier, int64_t* n_next,

@@ -423,7 +423,7 @@ extern "C" int mvs_compact_accepted_p2p(mvs_ctx* ctx, int64_t N, int64_t index_b
         if (!peer_records[d] || !peer_counts[d]) { mvs_set_error("mvs_compact_accepted_p2p: null peer pointer %d", d); return MVS_ERR_ARG; }
     MVS_CUDA_CHECK(cudaSetDevice(ctx->device));
     return mvs_launch_compact_p2p(ctx, N, index_base, c, nrm, ref, vis_mask, avg, count, xy, gate, bound, peer_records,
-                                  peer_counts, rank, world, wire, capacity, (cudaStream_t)stream);
+                                  peer_counts, rank, world, wire, capacity, nullptr, nullptr, (cudaStream_t)stream);
 }
 
 extern "C" int mvs_wire_bytes(const mvs_ctx* ctx, int wire) {

@@ -151,7 +151,8 @@ void mvs_pmvs_release(mvs_ctx* ctx);
 int mvs_launch_compact_p2p(mvs_ctx* ctx, int64_t N, int64_t index_base, const double* c, const double* nrm,
                            const int32_t* ref, const uint64_t* vis, const double* avg, const int32_t* count,
                            const double* xy, const uint8_t* gate, int bound, void* const* peer_records,
-                           int64_t* const* peer_counts, int rank, int world, int wire, int64_t capacity, cudaStream_t s);
+                           int64_t* const* peer_counts, int rank, int world, int wire, int64_t capacity,
+                           const int64_t* index_arr, const int32_t* px, cudaStream_t s);
 int mvs_launch_records_expand(mvs_ctx* ctx, const void* wire, int64_t n, void* records, cudaStream_t s);
 int mvs_launch_compact(mvs_ctx* ctx, int64_t N, int64_t index_base, const double* c, const double* nrm, const int32_t* ref,
                        const uint64_t* vis, const double* avg, const int32_t* count, const double* xy, const uint8_t* gate,

@@ -81,6 +81,45 @@ class DeviceBackend:
                                         C.c_void_p(self._n.data_ptr()), self._stream()), "mvs_round_score")
         return recs, self._n
 
+    # -- fused exchange (symmetric-memory inboxes, see mvs_compact_accepted_p2p) ----------------------
+    WIRE_COMPACT = 1
+
+    def p2p_setup(self, capacity, world, group):
+        """(Re)allocate this GPU's inbox of world x capacity compact wire records + world counts as
+        symmetric memory and exchange the peer mappings.  Collective over ``group``."""
+        import torch.distributed._symmetric_memory as symm_mem
+        t = self.torch
+        wb = self.lib.mvs_wire_bytes(self.ctx._h, self.WIRE_COMPACT)
+        inbox = symm_mem.empty(world * capacity * wb, dtype=t.uint8, device=self.device)
+        counts = symm_mem.empty(world, dtype=t.int64, device=self.device)
+        h = symm_mem.rendezvous(inbox, group)
+        h2 = symm_mem.rendezvous(counts, group)
+        self._p2p = dict(inbox=inbox, counts=counts, h=h, h2=h2, cap=capacity, world=world, wb=wb,
+                         recs=(C.c_void_p * world)(*[int(x) for x in h.buffer_ptrs]),
+                         cnts=(C.c_void_p * world)(*[int(x) for x in h2.buffer_ptrs]))
+        return self._p2p
+
+    def score_p2p(self, frontier, begin, end, rank):
+        """Score the shard and store its passing records into every GPU's inbox; returns the gathered
+        FULL records of all ranks in slot order and the per-rank counts (one host sync for the counts)."""
+        p = self._p2p
+        t = self.torch
+        p["h"].barrier(channel=0)                                 # every inbox is free again
+        _check(self.lib.mvs_round_score_p2p(self.ctx._h, C.c_void_p(frontier.data_ptr()), begin, end, self.min_ncc, self.wid,
+                                            self.bound, self.scale, p["recs"], p["cnts"], rank, p["world"], self.WIRE_COMPACT,
+                                            p["cap"], self._stream()), "mvs_round_score_p2p")
+        p["h"].barrier(channel=1)                                 # every rank's records and counts have landed
+        counts = p["counts"].cpu().tolist()
+        wb, cap = p["wb"], p["cap"]
+        parts = [p["inbox"][r * cap * wb: (r * cap + counts[r]) * wb] for r in range(p["world"]) if counts[r] > 0]
+        total = int(sum(counts))
+        full = self.empty(max(total, 1))
+        if total:
+            wire = t.cat(parts) if len(parts) > 1 else parts[0]
+            _check(self.lib.mvs_records_expand(self.ctx._h, self.WIRE_COMPACT, C.c_void_p(wire.data_ptr()), total,
+                                               C.c_void_p(full.data_ptr()), self._stream()), "mvs_records_expand")
+        return full[:total], counts
+
     def commit(self, records):
         n = records.shape[0]
         nxt = self.empty(max(n, 1))
@@ -99,9 +138,14 @@ class RoundDriver:
     """Runs rounds over a backend; with ``world > 1`` candidates are sharded by index and the
     accepted records all-gathered (torch.distributed: NCCL on GPUs, gloo in CPU tests)."""
 
-    def __init__(self, backend, rank=0, world=1, group=None, timing=False):
+    def __init__(self, backend, rank=0, world=1, group=None, timing=False, exchange="collective"):
+        """exchange: "collective" = all-gather of (counts, records) through torch.distributed (NCCL on GPUs,
+        gloo in the CPU tests); "p2p" = the compaction stores the records straight into every GPU's
+        symmetric-memory inbox over NVLink (mvs_round_score_p2p), no collective call for the payload."""
         self.b = backend
         self.rank, self.world, self.group = rank, world, group
+        self.exchange = exchange if world > 1 else "collective"
+        self._p2p_cap = 0
         self.stats = []
         self.timing = timing and hasattr(backend, "torch")       # CUDA events around every round
         self._events = []
@@ -143,10 +187,18 @@ class RoundDriver:
     def _round(self, frontier):
         M = self.b.generate(frontier)
         begin, end = shard_bounds(M, self.rank, self.world)
-        recs, n_local = self.b.score(frontier, begin, end)
-        if self.world > 1:
+        if self.exchange == "p2p":
+            need = (M + self.world - 1) // self.world + 1         # largest shard: the same number on every rank
+            if need > self._p2p_cap:
+                import torch.distributed as dist
+                self._p2p_cap = max(2 * need, 4096)
+                self.b.p2p_setup(self._p2p_cap, self.world, self.group if self.group is not None else dist.group.WORLD)
+            allrecs, counts = self.b.score_p2p(frontier, begin, end, self.rank)
+        elif self.world > 1:
+            recs, n_local = self.b.score(frontier, begin, end)
             allrecs, counts = self._gather(recs, n_local)
         else:
+            recs, n_local = self.b.score(frontier, begin, end)
             allrecs = recs[: int(n_local.item())]
             counts = [allrecs.shape[0]]
         nxt = self.b.commit(allrecs)

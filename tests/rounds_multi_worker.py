@@ -1,6 +1,8 @@
 """Worker of tests/test_rounds_multi_gpu.py: run under torchrun, one process per GPU.  Every rank runs the
-round driver with the candidates sharded over the ranks (NCCL all-gather of accepted records per round)
-and, in a second context, unsharded; the accepted records and the cell tables must be identical."""
+round driver with the candidates sharded over the ranks -- once with the NCCL all-gather of accepted
+records, once with the exchange fused into the compaction (P2P stores into symmetric-memory inboxes,
+compact wire records expanded on the receiver) -- and, in a third context, unsharded; the accepted records
+and the cell tables must be identical in all three."""
 import os
 import sys
 
@@ -25,14 +27,15 @@ def main():
     ns = int(e["n_seeds"])
     seeds = records.make_records(V, e["c"][:ns], e["n"][:ns], e["xy"][:ns], e["avg"][:ns], e["ref"][:ns], e["vis"][:ns])
     out = {}
-    for name, (r, w) in (("sharded", (rank, world)), ("single", (0, 1))):
+    for name, (r, w, ex) in (("sharded", (rank, world, "collective")), ("p2p", (rank, world, "p2p")), ("single", (0, 1, "collective"))):
         with mvs_b200.MvsContext(s["rgb"], s["K"], s["R"], s["t"], Rrt=s["Rrt"], device=local) as ctx:
             be = DeviceBackend(ctx, cell_size=2, scale=float(e["scale"]), bound=int(e["bound"]), table=e["table_before"])
-            drv = RoundDriver(be, rank=r, world=w)
+            drv = RoundDriver(be, rank=r, world=w, exchange=ex)
             acc = drv.run(be.to_device(seeds), max_rounds=6)
             out[name] = (np.concatenate([be.to_host(a) for a in acc]) if acc else None, be.table(), drv.stats)
-    a, b = out["sharded"], out["single"]
-    same = (a[0] is not None and b[0] is not None and a[0].tobytes() == b[0].tobytes() and np.array_equal(a[1], b[1]))
+    a, b, p = out["sharded"], out["single"], out["p2p"]
+    same = (a[0] is not None and b[0] is not None and a[0].tobytes() == b[0].tobytes() and np.array_equal(a[1], b[1]) and
+            p[0] is not None and p[0].tobytes() == b[0].tobytes() and np.array_equal(p[1], b[1]))
     shards = [st["shard"] for st in a[2]]
     ok = torch.tensor([int(same and len(a[0]) > 50)], device="cuda")
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
