@@ -12,7 +12,7 @@
 //                 HarrisFeatures.py:128; writes xy, the packed anchor, the empty result of
 //                 rejected hypotheses; counts the hypothesis into its tile's histogram
 //   (exclusive scan of the histogram, scan.cu)
-//   bin_scatter : order[pos] = hypothesis index, sanchor[pos] = its anchor
+//   bin_scatter : entry[pos] = (hypothesis index, anchor)
 // The order inside a tile depends on atomic arrival, the RESULTS do not: each hypothesis
 // is scored independently and written to its own output slot.
 #include "project.cuh"
@@ -23,7 +23,19 @@ __global__ void __launch_bounds__(256)
                 const int32_t* __restrict__ ref, int tiles_x, int n_tiles, int32_t* __restrict__ hist,
                 int32_t* __restrict__ key, int32_t* __restrict__ rank, uint32_t* __restrict__ anchor,
                 uint64_t* __restrict__ vis_out, double* __restrict__ avg_out, int32_t* __restrict__ count_out,
-                double* __restrict__ xy_out, float* __restrict__ ncc_out) {
+                double* __restrict__ xy_out, float* __restrict__ ncc_out, int cams_in_smem) {
+    // cameras go to shared memory once per CTA: every thread reads the 128-byte record of ITS reference
+    // view (32 different L1 lines per warp instruction when read from global memory)
+    extern __shared__ __align__(16) unsigned char s_cam_raw[];
+    const CamProj* cam_src = cams;
+    if (cams_in_smem) {
+        CamProj* s_cam = reinterpret_cast<CamProj*>(s_cam_raw);
+        const double* src = reinterpret_cast<const double*>(cams);
+        double* dst = reinterpret_cast<double*>(s_cam);
+        for (int i = threadIdx.x; i < V * (int)(sizeof(CamProj) / sizeof(double)); i += blockDim.x) dst[i] = src[i];
+        __syncthreads();
+        cam_src = s_cam;
+    }
     const int mw = (V + 63) >> 6;
     for (int64_t h = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; h < N; h += (int64_t)gridDim.x * blockDim.x) {
         const int r = __ldg(ref + h);
@@ -31,7 +43,7 @@ __global__ void __launch_bounds__(256)
         int row = 0, col = 0;
         bool valid = false;
         if (r >= 0 && r < V) {
-            project_ref(cams[r], __ldg(c + 3 * h), __ldg(c + 3 * h + 1), __ldg(c + 3 * h + 2), x, y);
+            project_ref(cam_src[r], __ldg(c + 3 * h), __ldg(c + 3 * h + 1), __ldg(c + 3 * h + 2), x, y);
             valid = window_anchor(x, y, H, W, wid, row, col);
         }
         if (xy_out) {
@@ -58,12 +70,10 @@ __global__ void __launch_bounds__(256)
 
 __global__ void __launch_bounds__(256)
     bin_scatter(int64_t N, const int32_t* __restrict__ hist_excl, const int32_t* __restrict__ key,
-                const int32_t* __restrict__ rank, const uint32_t* __restrict__ anchor, int32_t* __restrict__ order,
-                uint32_t* __restrict__ sanchor) {
+                const int32_t* __restrict__ rank, const uint32_t* __restrict__ anchor, uint2* __restrict__ entry) {
     for (int64_t h = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; h < N; h += (int64_t)gridDim.x * blockDim.x) {
         const int pos = hist_excl[key[h]] + rank[h];
-        order[pos] = (int32_t)h;
-        sanchor[pos] = anchor[h];
+        entry[pos] = make_uint2((uint32_t)h, anchor[h]);   // one 8-byte scattered store per hypothesis
     }
 }
 
@@ -82,8 +92,7 @@ int mvs_bin_hypotheses(mvs_ctx* ctx, int64_t N, const double* c, const int32_t* 
         if ((rc = mvs_ensure((void**)&ctx->d_bin_hist, &ctx->bin_hist_bytes, sizeof(int32_t) * (n_tiles + 2), "tile histogram")) != MVS_OK ||
             (rc = mvs_ensure((void**)&ctx->d_bin_key, &ctx->bin_key_bytes, sizeof(int32_t) * N, "tile keys")) != MVS_OK ||
             (rc = mvs_ensure((void**)&ctx->d_bin_rank, &ctx->bin_rank_bytes, sizeof(int32_t) * N, "tile ranks")) != MVS_OK ||
-            (rc = mvs_ensure((void**)&ctx->d_bin_order, &ctx->bin_order_bytes, sizeof(int32_t) * N, "order")) != MVS_OK ||
-            (rc = mvs_ensure((void**)&ctx->d_bin_sanchor, &ctx->bin_sanchor_bytes, sizeof(uint32_t) * N, "sorted anchors")) != MVS_OK ||
+            (rc = mvs_ensure((void**)&ctx->d_bin_entry, &ctx->bin_entry_bytes, sizeof(uint2) * N, "ordered entries")) != MVS_OK ||
             (rc = mvs_ensure((void**)&ctx->d_bin_scan, &ctx->bin_scan_bytes, sizeof(int64_t) * ((n_tiles + 1 + 1023) / 1024 + 2), "scan")) != MVS_OK)
             return rc;
         MVS_CUDA_CHECK(cudaMemsetAsync(ctx->d_bin_hist, 0, sizeof(int32_t) * (n_tiles + 2), s));
@@ -91,16 +100,19 @@ int mvs_bin_hypotheses(mvs_ctx* ctx, int64_t N, const double* c, const int32_t* 
     int64_t blocks = (N + 255) / 256;
     const int64_t cap = (int64_t)ctx->sm_count * 16;
     if (blocks > cap) blocks = cap;
-    bin_project<<<(int)blocks, 256, 0, s>>>(ctx->d_cam, ctx->V, ctx->H, ctx->W, wid, N, c, ref, tiles_x, n_tiles,
-                                            sort ? ctx->d_bin_hist : nullptr, ctx->d_bin_key, ctx->d_bin_rank,
-                                            ctx->d_bin_anchor, vis, avg, count, xy, ncc);
+    const size_t cam_bytes = sizeof(CamProj) * (size_t)ctx->V;
+    const int cams_in_smem = cam_bytes <= 48 * 1024 && N >= 4096;      // up to 384 views; tiny batches skip the staging
+    bin_project<<<(int)blocks, 256, cams_in_smem ? cam_bytes : 0, s>>>(ctx->d_cam, ctx->V, ctx->H, ctx->W, wid, N, c, ref, tiles_x,
+                                                                      n_tiles, sort ? ctx->d_bin_hist : nullptr, ctx->d_bin_key,
+                                                                      ctx->d_bin_rank, ctx->d_bin_anchor, vis, avg, count, xy, ncc,
+                                                                      cams_in_smem);
     ctx->launches++;
     if (sort) {
         int64_t* d_total = ctx->d_bin_scan + (n_tiles + 1 + 1023) / 1024;
         if ((rc = mvs_exclusive_scan_i32(ctx->d_bin_hist, n_tiles + 1, ctx->d_bin_scan, d_total, s)) != MVS_OK) return rc;
         ctx->launches += 3;
         bin_scatter<<<(int)blocks, 256, 0, s>>>(N, ctx->d_bin_hist, ctx->d_bin_key, ctx->d_bin_rank, ctx->d_bin_anchor,
-                                                ctx->d_bin_order, ctx->d_bin_sanchor);
+                                                (uint2*)ctx->d_bin_entry);
         ctx->launches++;
     }
     MVS_CUDA_CHECK(cudaGetLastError());

@@ -228,8 +228,8 @@ extern "C" int mvs_destroy(mvs_ctx* ctx) {
     if (ctx->d_stage) cudaFree(ctx->d_stage);
     if (ctx->d_tiles) cudaFree(ctx->d_tiles);
     mvs_pmvs_release(ctx);
-    void* more[] = {ctx->d_smap, ctx->d_vmap, ctx->d_bin_hist, ctx->d_bin_key, ctx->d_bin_rank, ctx->d_bin_order,
-                    ctx->d_bin_anchor, ctx->d_bin_sanchor, ctx->d_bin_scan};
+    void* more[] = {ctx->d_smap, ctx->d_vmap, ctx->d_bin_hist, ctx->d_bin_key, ctx->d_bin_rank, ctx->d_bin_entry,
+                    ctx->d_bin_anchor, ctx->d_bin_scan};
     for (void* b : more)
         if (b) cudaFree(b);
     void* bufs[] = {ctx->d_cells, ctx->d_claim, ctx->d_counts, ctx->d_scan, ctx->cand_slot, ctx->cand_parent, ctx->cand_c,

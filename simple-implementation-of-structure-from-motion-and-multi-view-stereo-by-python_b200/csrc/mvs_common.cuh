@@ -55,11 +55,10 @@ struct mvs_ctx {
     int32_t* d_bin_hist;   // [tiles + 2]
     int32_t* d_bin_key;    // [N]
     int32_t* d_bin_rank;   // [N]
-    int32_t* d_bin_order;  // [N] hypothesis index per sorted position
+    void* d_bin_entry;     // [N] uint2 (hypothesis index, anchor) per ordered position
     uint32_t* d_bin_anchor;   // [N] row<<16 | col per hypothesis (MVS_ANCHOR_INVALID = rejected)
-    uint32_t* d_bin_sanchor;  // [N] the same per sorted position
     int64_t* d_bin_scan;
-    size_t bin_hist_bytes, bin_key_bytes, bin_rank_bytes, bin_order_bytes, bin_anchor_bytes, bin_sanchor_bytes,
+    size_t bin_hist_bytes, bin_key_bytes, bin_rank_bytes, bin_entry_bytes, bin_anchor_bytes,
         bin_scan_bytes;
     // optional CUDA-event bracket around the scoring kernel (mvs_profile_enable)
     int profile;
@@ -138,7 +137,7 @@ int mvs_launch_score_refexact(mvs_ctx* ctx, int64_t N, const double* c, const in
                               uint64_t* vis, double* avg, int32_t* count, double* xy, float* ncc, cudaStream_t s);
 int mvs_build_window_maps(mvs_ctx* ctx, int wid, cudaStream_t s);
 // project + validate every hypothesis (writes xy and, for rejected ones, the empty result),
-// optionally order them by anchor tile; leaves anchors / order in ctx->d_bin_*
+// optionally order them by anchor tile; leaves anchors / ordered entries in ctx->d_bin_*
 int mvs_bin_hypotheses(mvs_ctx* ctx, int64_t N, const double* c, const int32_t* ref, int wid, bool sort, uint64_t* vis,
                        double* avg, int32_t* count, double* xy, float* ncc, cudaStream_t s);
 int mvs_launch_score_pmvs(mvs_ctx* ctx, int64_t N, const double* c, const double* nrm, const int32_t* ref,

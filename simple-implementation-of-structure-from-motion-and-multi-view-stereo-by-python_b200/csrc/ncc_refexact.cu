@@ -434,11 +434,11 @@ __device__ __forceinline__ void score_block(const ScoreArgs& A, const uint32_t (
 // share L1 lines; two neighbouring positions with the same (row, pixel group) are scored
 // as one block with shared loads.  anchors[i] = row<<16|col of position i
 // (MVS_ANCHOR_INVALID: rejected, result already written by bin_project); order[i] =
-// hypothesis index (NULL: identity).
+// hypothesis index (NULL: identity) -- packed as entries[i] = (index, anchor) for ordered batches.
 // ---------------------------------------------------------------------------------
 template <int WID, int LPH, int GS, int MINB, bool WANT_NCC>
 __global__ void __launch_bounds__(256, MINB)
-    ncc_score_gather(const ScoreArgs A, int64_t N, const uint32_t* __restrict__ anchors, const int32_t* __restrict__ order) {
+    ncc_score_gather(const ScoreArgs A, int64_t N, const uint32_t* __restrict__ anchors, const uint2* __restrict__ entries) {
     constexpr int K = 2 * WID + 1;
     constexpr int NG = (K + 6) / 4;
     constexpr int HPW = 32 / LPH;
@@ -457,11 +457,22 @@ __global__ void __launch_bounds__(256, MINB)
         for (int it = 0; it < ITERS; ++it) {
             const int64_t i = i0 + 2 * ((it * 8 + wib) * HPW + sub);
             if (i >= N) continue;                          // the whole lane group leaves together
-            const uint32_t a0 = __ldg(anchors + i);
-            const uint32_t a1 = (i + 1 < N) ? __ldg(anchors + i + 1) : MVS_ANCHOR_INVALID;
+            uint32_t a0, a1 = MVS_ANCHOR_INVALID;
+            int64_t h0 = i, h1 = i + 1;
+            if (entries) {                                 // ordered batch: (hypothesis index, anchor) pairs
+                const uint2 e0 = __ldg(entries + i);
+                h0 = e0.x;
+                a0 = e0.y;
+                if (i + 1 < N) {
+                    const uint2 e1 = __ldg(entries + i + 1);
+                    h1 = e1.x;
+                    a1 = e1.y;
+                }
+            } else {
+                a0 = __ldg(anchors + i);
+                if (i + 1 < N) a1 = __ldg(anchors + i + 1);
+            }
             const bool ok0 = a0 != MVS_ANCHOR_INVALID, ok1 = a1 != MVS_ANCHOR_INVALID;
-            const int64_t h0 = order ? (int64_t)__ldg(order + i) : i;
-            const int64_t h1 = (order && ok1) ? (int64_t)__ldg(order + i + 1) : i + 1;
             const bool same = ok0 && ok1 && ((a0 >> 16) == (a1 >> 16)) &&
                               ((((int)(a0 & 0xffffu) - WID) >> 2) == (((int)(a1 & 0xffffu) - WID) >> 2));
             if (same) {
@@ -488,7 +499,7 @@ __global__ void __launch_bounds__(256, MINB)
 #endif
 
 template <int WID, int LPH, int GS, int MINB = MVS_K1_MINB>
-static int launch_gather_gs(mvs_ctx* ctx, const ScoreArgs& A, int64_t N, const uint32_t* anchors, const int32_t* order,
+static int launch_gather_gs(mvs_ctx* ctx, const ScoreArgs& A, int64_t N, const uint32_t* anchors, const uint2* entries,
                             cudaStream_t s) {
     // the per-view NCC dump is a parity/debug output: its stores are compiled out of the hot variant
     auto kern = A.ncc_out ? ncc_score_gather<WID, LPH, GS, MINB, true> : ncc_score_gather<WID, LPH, GS, MINB, false>;
@@ -496,7 +507,7 @@ static int launch_gather_gs(mvs_ctx* ctx, const ScoreArgs& A, int64_t N, const u
     const int64_t want = (N + chunk - 1) / chunk;
     const int64_t cap = (int64_t)ctx->sm_count * MINB * 8;
     const int blocks = (int)(want < cap ? want : cap);
-    kern<<<blocks, 256, 0, s>>>(A, N, anchors, order);
+    kern<<<blocks, 256, 0, s>>>(A, N, anchors, entries);
     return MVS_OK;
 }
 
@@ -511,25 +522,25 @@ static int k1_minb_override() {
 }
 
 template <int WID>
-static int launch_gather(mvs_ctx* ctx, const ScoreArgs& A, int64_t N, const uint32_t* anchors, const int32_t* order,
+static int launch_gather(mvs_ctx* ctx, const ScoreArgs& A, int64_t N, const uint32_t* anchors, const uint2* entries,
                          cudaStream_t s) {
     const int Q = ctx->Q;
-    if (Q <= 4) return launch_gather_gs<WID, 4, 0>(ctx, A, N, anchors, order, s);
-    if (Q <= 8) return launch_gather_gs<WID, 8, 0>(ctx, A, N, anchors, order, s);
+    if (Q <= 4) return launch_gather_gs<WID, 4, 0>(ctx, A, N, anchors, entries, s);
+    if (Q <= 8) return launch_gather_gs<WID, 8, 0>(ctx, A, N, anchors, entries, s);
     if (Q <= 16) {
         // the reference's own configuration (wid 5, dinoRing's 48 views): group stride as an immediate
         if (WID == 5 && Q == 12) {
             const int mb = k1_minb_override();
-            if (mb == 2) return launch_gather_gs<5, 16, 192, 2>(ctx, A, N, anchors, order, s);
-            if (mb == 4) return launch_gather_gs<5, 16, 192, 4>(ctx, A, N, anchors, order, s);
-            if (mb == 3) return launch_gather_gs<5, 16, 192, 3>(ctx, A, N, anchors, order, s);
-            return launch_gather_gs<5, 16, 192, 4>(ctx, A, N, anchors, order, s);
+            if (mb == 2) return launch_gather_gs<5, 16, 192, 2>(ctx, A, N, anchors, entries, s);
+            if (mb == 4) return launch_gather_gs<5, 16, 192, 4>(ctx, A, N, anchors, entries, s);
+            if (mb == 3) return launch_gather_gs<5, 16, 192, 3>(ctx, A, N, anchors, entries, s);
+            return launch_gather_gs<5, 16, 192, 4>(ctx, A, N, anchors, entries, s);
         }
-        return launch_gather_gs<WID, 16, 0>(ctx, A, N, anchors, order, s);
+        return launch_gather_gs<WID, 16, 0>(ctx, A, N, anchors, entries, s);
     }
-    if (WID == 5 && Q == 32) return launch_gather_gs<WID, 32, 512>(ctx, A, N, anchors, order, s);
-    if (WID == 5 && Q == 64) return launch_gather_gs<WID, 32, 1024>(ctx, A, N, anchors, order, s);
-    return launch_gather_gs<WID, 32, 0>(ctx, A, N, anchors, order, s);
+    if (WID == 5 && Q == 32) return launch_gather_gs<WID, 32, 512>(ctx, A, N, anchors, entries, s);
+    if (WID == 5 && Q == 64) return launch_gather_gs<WID, 32, 1024>(ctx, A, N, anchors, entries, s);
+    return launch_gather_gs<WID, 32, 0>(ctx, A, N, anchors, entries, s);
 }
 
 int mvs_launch_score_refexact(mvs_ctx* ctx, int64_t N, const double* c, const int32_t* ref, double thr, int wid,
@@ -543,8 +554,8 @@ int mvs_launch_score_refexact(mvs_ctx* ctx, int64_t N, const double* c, const in
     if ((rc = mvs_build_window_maps(ctx, wid, s)) != MVS_OK) return rc;
     const bool sort = N >= MVS_SORT_MIN;
     if ((rc = mvs_bin_hypotheses(ctx, N, c, ref, wid, sort, vis, avg, count, xy, ncc, s)) != MVS_OK) return rc;
-    const uint32_t* anchors = sort ? ctx->d_bin_sanchor : ctx->d_bin_anchor;
-    const int32_t* order = sort ? ctx->d_bin_order : nullptr;
+    const uint32_t* anchors = ctx->d_bin_anchor;
+    const uint2* entries = sort ? (const uint2*)ctx->d_bin_entry : nullptr;
     ScoreArgs A;
     A.gray4 = ctx->d_gray; A.smap = ctx->d_smap; A.vmap = ctx->d_vmap;
     A.V = ctx->V; A.Vp = ctx->Vp; A.Q = ctx->Q; A.W = ctx->W;
@@ -553,13 +564,13 @@ int mvs_launch_score_refexact(mvs_ctx* ctx, int64_t N, const double* c, const in
     const int pslot = (int)(ctx->prof_n % MVS_PROF_RING);
     if (ctx->profile) MVS_CUDA_CHECK(cudaEventRecord(ctx->prof_ev[2 * pslot], s));
     switch (wid) {
-        case 1: rc = launch_gather<1>(ctx, A, N, anchors, order, s); break;
-        case 2: rc = launch_gather<2>(ctx, A, N, anchors, order, s); break;
-        case 3: rc = launch_gather<3>(ctx, A, N, anchors, order, s); break;
-        case 4: rc = launch_gather<4>(ctx, A, N, anchors, order, s); break;
-        case 5: rc = launch_gather<5>(ctx, A, N, anchors, order, s); break;
-        case 6: rc = launch_gather<6>(ctx, A, N, anchors, order, s); break;
-        default: rc = launch_gather<7>(ctx, A, N, anchors, order, s); break;
+        case 1: rc = launch_gather<1>(ctx, A, N, anchors, entries, s); break;
+        case 2: rc = launch_gather<2>(ctx, A, N, anchors, entries, s); break;
+        case 3: rc = launch_gather<3>(ctx, A, N, anchors, entries, s); break;
+        case 4: rc = launch_gather<4>(ctx, A, N, anchors, entries, s); break;
+        case 5: rc = launch_gather<5>(ctx, A, N, anchors, entries, s); break;
+        case 6: rc = launch_gather<6>(ctx, A, N, anchors, entries, s); break;
+        default: rc = launch_gather<7>(ctx, A, N, anchors, entries, s); break;
     }
     if (ctx->profile) {
         MVS_CUDA_CHECK(cudaEventRecord(ctx->prof_ev[2 * pslot + 1], s));
