@@ -196,14 +196,10 @@ class CellTable(object):
 
     def reconstruct_from_Q(self):
         """MVS2.py:159-173: every distinct patch once, in table-scan order."""
-        seen, points_3d, colors = set(), [], []
-        for key in sorted(self.Q_table):                   # (view, x-cell, y-cell): the reference's scan order
-            for p in self.Q_table[key]:
-                if id(p) not in seen:
-                    seen.add(id(p))
-                    points_3d.append(p.c)
-                    colors.append(p.color)
-        return points_3d, colors
+        import itertools
+        # first occurrence in (view, x-cell, y-cell) scan order; MyPatch hashes by identity
+        distinct = dict.fromkeys(itertools.chain.from_iterable(self.Q_table[key] for key in sorted(self.Q_table)))
+        return [p.c for p in distinct], [p.color for p in distinct]
 
 
 def is_patch_neighbor(patch, non_finished_patch, threshold=0.2):
@@ -246,15 +242,33 @@ def _patches_to_records(patches, V):
 
 
 def _records_to_patches(recs, imgs, V):
-    out = []
+    """Device patch records -> MyPatch objects (the reference's carrier type).  Field extraction is
+    done array-wise; only the object construction itself is per patch."""
+    n = len(recs)
+    if n == 0:
+        return []
     vis = unpack_vis(recs["vis"], V)
-    for k in range(len(recs)):
-        r = recs[k]
-        x, y = float(r["xy"][0]), float(r["xy"][1])
-        color = imgs[int(r["ref"])][int(r["px"][1])][int(r["px"][0])] if r["px"][0] >= 0 else np.zeros(3)
-        p = MyPatch(np.array(r["c"]), np.array(r["n"]), int(r["ref"]), [[int(v), x, y] for v in np.nonzero(vis[k])[0]],
-                    color, None)
-        p.avg_ncc_score = float(r["avg"])
+    rows, views = np.nonzero(vis)                              # row-major: ascending view index inside a patch
+    starts = np.searchsorted(rows, np.arange(n + 1))
+    views = views.tolist()
+    c = np.ascontiguousarray(recs["c"])
+    nrm = np.ascontiguousarray(recs["n"])
+    xy = recs["xy"].tolist()
+    ref = recs["ref"].tolist()
+    avg = recs["avg"].tolist()
+    px = recs["px"]
+    has_px = px[:, 0] >= 0
+    colors = np.zeros((n, 3), dtype=imgs[0].dtype)
+    if has_px.any():
+        stack_ref = np.asarray(recs["ref"])[has_px]
+        pr, pc = px[has_px, 1], px[has_px, 0]
+        colors[has_px] = [imgs[r][y][x] for r, y, x in zip(stack_ref.tolist(), pr.tolist(), pc.tolist())]
+    out = []
+    for k in range(n):
+        x, y = xy[k]
+        p = MyPatch(c[k].copy(), nrm[k].copy(), ref[k], [[v, x, y] for v in views[starts[k]:starts[k + 1]]],
+                    colors[k] if has_px[k] else np.zeros(3), None)
+        p.avg_ncc_score = avg[k]
         out.append(p)
     return out
 
