@@ -12,7 +12,6 @@
 #define MVS_MAX_PEERS 16
 #define MVS_PROF_RING 64
 #define MVS_ANCHOR_INVALID 0xffffffffu
-#define MVS_BIN_SHIFT 3          // anchor tiles of 8x8 pixels
 #define MVS_SORT_MIN 8192        // batches smaller than this are scored in input order
 
 // One view's projection parameters as the scorer reads them (128 B, fp64).
