@@ -156,11 +156,19 @@ __global__ void __launch_bounds__(256)
         room = room < 0 ? 0 : room;
         const int nrec = (int)(room < total ? room : total);
         const int nwords = nrec * rec_words;
-        const uint64_t* src = reinterpret_cast<const uint64_t*>(s_rec);
         const int64_t off = ((int64_t)P.rank * capacity + out) * rec_bytes;
-        for (int t = threadIdx.x; t < nwords; t += 256) {
-            const uint64_t wv = src[t];
-            for (int d = 0; d < P.world; ++d) reinterpret_cast<uint64_t*>(P.rec[d] + off)[t] = wv;
+        if ((rec_bytes & 15) == 0) {                       // 16-byte stores (64-byte compact wire records at V <= 64)
+            const uint4* src = reinterpret_cast<const uint4*>(s_rec);
+            for (int t = threadIdx.x; t < (nwords >> 1); t += 256) {
+                const uint4 wv = src[t];
+                for (int d = 0; d < P.world; ++d) reinterpret_cast<uint4*>(P.rec[d] + off)[t] = wv;
+            }
+        } else {
+            const uint64_t* src = reinterpret_cast<const uint64_t*>(s_rec);
+            for (int t = threadIdx.x; t < nwords; t += 256) {
+                const uint64_t wv = src[t];
+                for (int d = 0; d < P.world; ++d) reinterpret_cast<uint64_t*>(P.rec[d] + off)[t] = wv;
+            }
         }
         out += total;
         __syncthreads();
