@@ -127,9 +127,10 @@ struct __align__(16) ViewAffine {
 // Bilinear sample through the gather path.  (u0, v0) = integer tap origin (pixel centres at
 // integers), (fu, fv) = fractions.  Returns the value in [0,1] and whether all four taps are
 // inside the image.
-__device__ __forceinline__ float tap4(cudaTextureObject_t tex, float2 off, float u0, float v0, float fu, float fv, bool front,
-                                      float wm2, float hm2, bool& ok) {
-    ok = front && (u0 >= 0.0f) && (u0 <= wm2) && (v0 >= 0.0f) && (v0 <= hm2);       // inside the VIEW, not the atlas
+__device__ __forceinline__ float tap4(const bool checked, cudaTextureObject_t tex, float2 off, float u0, float v0, float fu,
+                                      float fv, bool front, float wm2, float hm2, bool& ok) {
+    // inside the VIEW, not the atlas; an unchecked ("safe") view is known to be inside
+    ok = !checked || (front && (u0 >= 0.0f) && (u0 <= wm2) && (v0 >= 0.0f) && (v0 <= hm2));
     u0 += off.x;
     v0 += off.y;
     // the footprint of a gather at (u0+1, v0+1) is texels (u0..u0+1, v0..v0+1); the centre of
@@ -225,7 +226,7 @@ __global__ void __launch_bounds__(32, MINB) ncc_score_pmvs(const PmvsArgs A, int
             }
 
             // prepare view v for this hypothesis into slot `slot` (executed by one lane per view)
-            auto stage_view = [&](int v, int slot) {
+            auto stage_view = [&](int v, int slot) -> bool {
                 const int cam = reduce_a ? r : v;          // MVS2.py:68: the reference camera for every view
                 const CamProj& cv = A.cams[cam];
                 const CamProjF& cf = A.camsf[cam];
@@ -255,11 +256,21 @@ __global__ void __launch_bounds__(32, MINB) ncc_score_pmvs(const PmvsArgs A, int
                 va.gyv = step * fmaf(dv, ry2, cf.fy * ry1);
                 va.pad = 0.0f;
                 s_view[wib][slot] = va;
+                // "safe" view: the whole mu x mu footprint provably stays inside the image and in front of
+                // the camera (bound on the tap offsets from the staged increments, 0.01 px of slack), so its
+                // taps need no per-tap bounds test
+                const float zmin = va.Z0 - HALF * (fabsf(va.hxZ) + fabsf(va.hyZ));
+                const float izm = __fdividef(1.0f, zmin);     // (an IEEE division's slow path would break the warp-uniformity proof below)
+                const float ru = HALF * (fabsf(va.gxu) + fabsf(va.gyu)) * izm + 0.01f;
+                const float rv = HALF * (fabsf(va.gxv) + fabsf(va.gyv)) * izm + 0.01f;
+                const float ucl = (float)uc, vcl = (float)vc;
+                return !reduce_a && (zmin > 0.0f) && (ucl - ru >= 0.0f) && (ucl + ru <= wm2 + 0.98f) && (vcl - rv >= 0.0f) &&
+                       (vcl + rv <= hm2 + 0.98f);
             };
 
             // Issue the taps of the view staged in `slot` (no warp-synchronous operation in here,
             // so the gathers of a whole batch of views are in flight together).
-            auto issue_view = [&](int slot, cudaTextureObject_t tex, float2 off, float (&val)[SPL], bool& ok_all) {
+            auto issue_view = [&](const bool checked, int slot, cudaTextureObject_t tex, float2 off, float (&val)[SPL], bool& ok_all) {
                 const float4* pv = reinterpret_cast<const float4*>(&s_view[wib][slot]);
                 const float4 q0 = pv[0], q1 = pv[1], q2 = pv[2];          // iu fu iv fv | Z0 hxZ hyZ gxu | gyu gxv gyv -
                 ok_all = true;
@@ -284,8 +295,8 @@ __global__ void __launch_bounds__(32, MINB) ncc_score_pmvs(const PmvsArgs A, int
                         front = z > 0.0f;
                     }
                     bool ok;
-                    val[q] = tap4(tex, off, u0, v0, fu, fv, front, wm2, hm2, ok);
-                    ok_all &= ok || !live[q];
+                    val[q] = tap4(checked, tex, off, u0, v0, fu, fv, front, wm2, hm2, ok);
+                    if (checked) ok_all &= ok || !live[q];
                 }
             };
 
@@ -294,17 +305,21 @@ __global__ void __launch_bounds__(32, MINB) ncc_score_pmvs(const PmvsArgs A, int
             float Sr = 0.0f, ssr = 0.0f;
             for (int w32 = 0; w32 < 2 * mw; ++w32) {       // 32 views per mask word
                 uint32_t word = 0u;
+                bool safe_lo = false, safe_hi = false;
                 if (hyp_ok) {                              // uniform across the warp
                     // ---- stage this block's 32 views (one lane each); block 0 also stages the reference view
                     __syncwarp();
-                    stage_view(min(w32 * 32 + lane, A.V - 1), lane);       // lanes past the last view shadow it
+                    const bool safe = stage_view(min(w32 * 32 + lane, A.V - 1), lane);   // lanes past the last view shadow it
+                    // one vote per half: every view of the half safe -> its taps skip the bounds tests
+                    safe_lo = __all_sync(FULL, safe || lane >= 16);
+                    safe_hi = __all_sync(FULL, safe || lane < 16);
                     if (w32 == 0 && r >= 32 && lane == 0) stage_view(r, 32);
                     __syncwarp();
                     if (w32 == 0) {
                         // ---- the reference view's own samples
                         bool ok_all;
                         float val[SPL];
-                        issue_view(r < 32 ? r : 32, A.tex[r], A.off[r], val, ok_all);
+                        issue_view(true, r < 32 ? r : 32, A.tex[r], A.off[r], val, ok_all);
                         hyp_ok = __all_sync(FULL, ok_all);
                         const float pivot = __shfl_sync(FULL, val[0], 0);
                         float s = 0.0f, ss = 0.0f;
@@ -331,6 +346,7 @@ __global__ void __launch_bounds__(32, MINB) ncc_score_pmvs(const PmvsArgs A, int
                         constexpr int TB = SPL == 1 ? 16 : (SPL == 2 ? 8 : 4);
                         uint32_t bad = 0u;                                   // bit j: some tap of view j is outside
                         __syncwarp();                                        // the previous half's readers are done
+                        if (half ? safe_hi : safe_lo) {                      // safe half: taps without bounds tests
 #pragma unroll
                         for (int j0 = 0; j0 < 16; j0 += TB) {
                             float val[TB][SPL];
@@ -338,7 +354,7 @@ __global__ void __launch_bounds__(32, MINB) ncc_score_pmvs(const PmvsArgs A, int
 #pragma unroll
                             for (int jj = 0; jj < TB; ++jj)
                                 // views past the last one re-sample it (branch-free); their sums are never scored
-                                issue_view(half * 16 + j0 + jj, c_tex[min(vbase + j0 + jj, A.V - 1)], c_off[min(vbase + j0 + jj, A.V - 1)], val[jj], okl[jj]);
+                                issue_view(false, half * 16 + j0 + jj, c_tex[min(vbase + j0 + jj, A.V - 1)], c_off[min(vbase + j0 + jj, A.V - 1)], val[jj], okl[jj]);
 #pragma unroll
                             for (int jj = 0; jj < TB; ++jj) {
                                 if (!okl[jj]) bad |= 1u << (j0 + jj);
@@ -346,6 +362,24 @@ __global__ void __launch_bounds__(32, MINB) ncc_score_pmvs(const PmvsArgs A, int
                                 for (int q = 0; q < SPL; ++q)
                                     if (live[q]) s_val[j0 + jj][lane + 32 * q] = val[jj][q];
                             }
+                        }
+                        } else {
+#pragma unroll
+                        for (int j0 = 0; j0 < 16; j0 += TB) {
+                            float val[TB][SPL];
+                            bool okl[TB];
+#pragma unroll
+                            for (int jj = 0; jj < TB; ++jj)
+                                // views past the last one re-sample it (branch-free); their sums are never scored
+                                issue_view(true, half * 16 + j0 + jj, c_tex[min(vbase + j0 + jj, A.V - 1)], c_off[min(vbase + j0 + jj, A.V - 1)], val[jj], okl[jj]);
+#pragma unroll
+                            for (int jj = 0; jj < TB; ++jj) {
+                                if (!okl[jj]) bad |= 1u << (j0 + jj);
+#pragma unroll
+                                for (int q = 0; q < SPL; ++q)
+                                    if (live[q]) s_val[j0 + jj][lane + 32 * q] = val[jj][q];
+                            }
+                        }
                         }
                         const uint32_t usable16 = ~__reduce_or_sync(FULL, bad);
                         __syncwarp();

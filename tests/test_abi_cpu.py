@@ -49,3 +49,32 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_mode_b_gathers_take_uniform_texture_handles(built_lib):
+    """The Mode B kernels rely on the texture handle being provably warp-uniform: otherwise ptxas wraps
+    every TLD4 in a per-lane "waterfall" loop (BRA.U.ANY), which serialises the gathers of a batch of
+    views (measured 1.4x slower).  The proof is fragile (an IEEE fp32 division before the gathers breaks
+    it), so the SASS is checked at build time."""
+    import shutil
+    import subprocess
+    from mvs_b200 import _lib
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    kernels = {}
+    name = None
+    for line in sass.splitlines():
+        if "Function :" in line:
+            name = line.split("Function :")[1].strip()
+            kernels[name] = [0, 0]
+        elif name and "TLD4" in line:
+            kernels[name][0] += 1
+        elif name and "BRA.U.ANY" in line:
+            kernels[name][1] += 1
+    pmvs = {k: v for k, v in kernels.items() if "ncc_score_pmvs" in k and "Lb0" in k}
+    assert pmvs, "no Mode B kernels found in the library"
+    for k, (tld4, waterfall) in pmvs.items():
+        assert tld4 > 0, k
+        assert waterfall <= 2, (k, tld4, waterfall)      # only the reference view's own handle may need one
