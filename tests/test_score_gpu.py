@@ -91,8 +91,11 @@ def test_other_window_sizes_against_oracle(golden, built_lib, wid):
     _compare(out, o["vis"], o["ncc"], o["avg"], V)
 
 
-@pytest.mark.parametrize("V,H,W", [(48, 480, 640), (70, 120, 200), (33, 97, 131), (130, 120, 160), (7, 120, 160), (260, 120, 160)])
-def test_synthetic_ring_against_oracle(built_lib, V, H, W):
+@pytest.mark.parametrize("V,H,W,N", [(48, 480, 640, 6000), (70, 120, 200, 6000), (33, 97, 131, 6000), (130, 120, 160, 6000),
+                                     (7, 120, 160, 6000), (260, 120, 160, 6000),
+                                     # >= 8192 hypotheses: the tile-ordered path with shared loads for neighbours
+                                     (33, 97, 131, 9000), (130, 120, 160, 9000), (7, 120, 160, 9000), (70, 120, 200, 20000)])
+def test_synthetic_ring_against_oracle(built_lib, V, H, W, N):
     """48-view 640x480 is the shape the headline metric is quoted on; 70 views needs two
     mask words; 33 x 97 x 131 has a view count and a width that are not multiples of 4; 130 and 260
     views take the 32-lane kernel through 2 and 3 passes of 128 views; 7 views the 4-lane one."""
@@ -100,7 +103,7 @@ def test_synthetic_ring_against_oracle(built_lib, V, H, W):
     from mvs_b200 import rings
     from oracle import mode_a
     rgb, K, R, t = rings.make_ring(V, H, W, seed=11)
-    c, n, ref = rings.surface_hypotheses(6000, K, R, t, seed=12)
+    c, n, ref = rings.surface_hypotheses(N, K, R, t, seed=12)
     cams = _oracle_cams(K, R, t)
     with mvs_b200.MvsContext(rgb, K, R, t, Rrt=cams.R) as ctx:
         out = ctx.score_host(c, ref, min_ncc=0.7, want_ncc=True)
