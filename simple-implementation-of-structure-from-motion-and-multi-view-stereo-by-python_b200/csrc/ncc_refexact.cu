@@ -27,6 +27,9 @@
 #include <stdlib.h>
 
 #define FULL 0xffffffffu
+#ifndef MVS_K1_ITERS
+#define MVS_K1_ITERS 4          // block pairs per lane group and CTA pass: chunk = 8 warps x groups x 2 x ITERS positions
+#endif
 
 // ---------------------------------------------------------------------------------
 // K0: RGB u8 [V,H,W,3] -> gray u8 [H][G][Vp][4].  cv2.cvtColor(BGR2GRAY) applied to an
@@ -442,7 +445,7 @@ __global__ void __launch_bounds__(256, MINB)
     constexpr int K = 2 * WID + 1;
     constexpr int NG = (K + 6) / 4;
     constexpr int HPW = 32 / LPH;
-    constexpr int ITERS = 4;
+    constexpr int ITERS = MVS_K1_ITERS;
     constexpr int CHUNK = 8 * HPW * 2 * ITERS;
     __shared__ __align__(16) uint32_t s_ref[8][HPW][2][K][NG];
 
@@ -503,7 +506,7 @@ static int launch_gather_gs(mvs_ctx* ctx, const ScoreArgs& A, int64_t N, const u
                             cudaStream_t s) {
     // the per-view NCC dump is a parity/debug output: its stores are compiled out of the hot variant
     auto kern = A.ncc_out ? ncc_score_gather<WID, LPH, GS, MINB, true> : ncc_score_gather<WID, LPH, GS, MINB, false>;
-    const int64_t chunk = 8 * (32 / LPH) * 2 * 4;
+    const int64_t chunk = 8 * (32 / LPH) * 2 * MVS_K1_ITERS;
     const int64_t want = (N + chunk - 1) / chunk;
     const int64_t cap = (int64_t)ctx->sm_count * MINB * 8;
     const int blocks = (int)(want < cap ? want : cap);
