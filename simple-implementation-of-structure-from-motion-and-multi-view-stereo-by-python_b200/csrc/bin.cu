@@ -18,6 +18,14 @@
 #include "project.cuh"
 #include "scan.cuh"
 
+// anchor tile = 2^TR rows x 2^TC pixel groups (8 rows x 2 groups = 8 x 8 pixels measured best)
+#ifndef MVS_TILE_ROWS_LOG2
+#define MVS_TILE_ROWS_LOG2 3
+#endif
+#ifndef MVS_TILE_GROUPS_LOG2
+#define MVS_TILE_GROUPS_LOG2 1
+#endif
+
 __global__ void __launch_bounds__(256)
     bin_project(const CamProj* __restrict__ cams, int V, int H, int W, int wid, int64_t N, const double* __restrict__ c,
                 const int32_t* __restrict__ ref, int tiles_x, int n_tiles, int32_t* __restrict__ hist,
@@ -61,7 +69,10 @@ __global__ void __launch_bounds__(256)
         if (hist) {
             // bins = (row, first pixel group of the window), ordered tile by tile (8 rows x 2 groups)
             const int cg = (col - wid) >> 2;
-            const int k = valid ? (((row >> 3) * tiles_x + (cg >> 1)) << 4) + ((row & 7) << 1) + (cg & 1) : n_tiles;
+            constexpr int TR = MVS_TILE_ROWS_LOG2, TC = MVS_TILE_GROUPS_LOG2;
+            const int k = valid ? (((row >> TR) * tiles_x + (cg >> TC)) << (TR + TC)) + ((row & ((1 << TR) - 1)) << TC) +
+                                      (cg & ((1 << TC) - 1))
+                                : n_tiles;
             key[h] = k;
             rank[h] = atomicAdd(hist + k, 1);
         }
@@ -86,8 +97,8 @@ int mvs_bin_hypotheses(mvs_ctx* ctx, int64_t N, const double* c, const int32_t* 
     }
     if ((rc = mvs_ensure((void**)&ctx->d_bin_anchor, &ctx->bin_anchor_bytes, sizeof(uint32_t) * N, "anchors")) != MVS_OK)
         return rc;
-    const int tiles_x = (ctx->W >> 3) + 1, tiles_y = (ctx->H >> 3) + 1;
-    const int n_tiles = tiles_x * tiles_y * 16;            // bins: 16 (row, pixel group) cells per tile
+    const int tiles_x = (((ctx->W + 3) >> 2) >> MVS_TILE_GROUPS_LOG2) + 1, tiles_y = (ctx->H >> MVS_TILE_ROWS_LOG2) + 1;
+    const int n_tiles = (tiles_x * tiles_y) << (MVS_TILE_ROWS_LOG2 + MVS_TILE_GROUPS_LOG2);   // bins: one per (row, pixel group)
     if (sort) {
         if ((rc = mvs_ensure((void**)&ctx->d_bin_hist, &ctx->bin_hist_bytes, sizeof(int32_t) * (n_tiles + 2), "tile histogram")) != MVS_OK ||
             (rc = mvs_ensure((void**)&ctx->d_bin_key, &ctx->bin_key_bytes, sizeof(int32_t) * N, "tile keys")) != MVS_OK ||
