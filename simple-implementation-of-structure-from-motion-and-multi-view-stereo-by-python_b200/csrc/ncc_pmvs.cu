@@ -657,25 +657,25 @@ int mvs_launch_score_pmvs(mvs_ctx* ctx, int64_t N, const double* c, const double
     const int g = group > 1 ? group : 1;
     const int64_t n_sets = (N + g - 1) / g;
     int64_t blocks = n_sets;                               // one warp per CTA
-    const int64_t cap = (int64_t)ctx->sm_count * 16 * 4;
+    const int64_t cap = (int64_t)ctx->sm_count * 32 * 4;
     if (blocks > cap) blocks = cap;
     const int pslot = (int)(ctx->prof_n % MVS_PROF_RING);
     if (ctx->profile) MVS_CUDA_CHECK(cudaEventRecord(ctx->prof_ev[2 * pslot], s));
     static int minb = -1;                                  // MVS_K2_MINB: resident warps per SM (tuning knob)
     if (minb < 0) {
         const char* e = getenv("MVS_K2_MINB");
-        minb = e ? atoi(e) : 16;
+        minb = e ? atoi(e) : 32;                           // 32 one-warp CTAs per SM (64 registers) measured best
     }
 #define PMVS_LAUNCH(MU_)                                                         \
     case MU_:                                                                    \
         if (flags & MVS_PMVS_REDUCE_TO_REFEXACT)                                 \
             ncc_score_pmvs<MU_, true, 16><<<(int)blocks, 32, 0, s>>>(A, N);      \
-        else if (minb == 20)                                                     \
-            ncc_score_pmvs<MU_, false, 20><<<(int)blocks, 32, 0, s>>>(A, N);     \
+        else if (minb == 16)                                                     \
+            ncc_score_pmvs<MU_, false, 16><<<(int)blocks, 32, 0, s>>>(A, N);     \
         else if (minb == 24)                                                     \
             ncc_score_pmvs<MU_, false, 24><<<(int)blocks, 32, 0, s>>>(A, N);     \
         else                                                                     \
-            ncc_score_pmvs<MU_, false, 16><<<(int)blocks, 32, 0, s>>>(A, N);     \
+            ncc_score_pmvs<MU_, false, 32><<<(int)blocks, 32, 0, s>>>(A, N);     \
         break;
     switch (mu) {
         PMVS_LAUNCH(3) PMVS_LAUNCH(5) PMVS_LAUNCH(7) PMVS_LAUNCH(9) PMVS_LAUNCH(11)
