@@ -127,16 +127,15 @@ struct __align__(16) ViewAffine {
 // Bilinear sample through the gather path.  (u0, v0) = integer tap origin (pixel centres at
 // integers), (fu, fv) = fractions.  Returns the value in [0,1] and whether all four taps are
 // inside the image.
-__device__ __forceinline__ float tap4(const bool checked, cudaTextureObject_t tex, float2 off, float u0, float v0, float fu,
+__device__ __forceinline__ float tap4(const bool checked, cudaTextureObject_t tex, float2 off, float uc1, float vc1, float fu,
                                       float fv, bool front, float wm2, float hm2, bool& ok) {
-    // inside the VIEW, not the atlas; an unchecked ("safe") view is known to be inside
-    ok = !checked || (front && (u0 >= 0.0f) && (u0 <= wm2) && (v0 >= 0.0f) && (v0 <= hm2));
-    u0 += off.x;
-    v0 += off.y;
-    // the footprint of a gather at (u0+1, v0+1) is texels (u0..u0+1, v0..v0+1); the centre of
-    // the 2x2 block is the robust coordinate.  Components: x=(0,1) y=(1,1) z=(1,0) w=(0,0) as
-    // (column offset, row offset).
-    const float4 g = tex2Dgather<float4>(tex, ok ? u0 + 1.0f : off.x + 1.0f, ok ? v0 + 1.0f : off.y + 1.0f, 0);
+    // (uc1, vc1) = tap origin + tile origin + 1: the centre of the 2x2 gather footprint inside the atlas.
+    // Bounds are tested against the VIEW's tile, not the atlas; an unchecked ("safe") view is known to be
+    // inside, and the texture's clamp addressing makes the fetch of a rejected tap harmless.
+    ok = !checked || (front && (uc1 >= off.x + 1.0f) && (uc1 <= off.x + 1.0f + wm2) && (vc1 >= off.y + 1.0f) &&
+                      (vc1 <= off.y + 1.0f + hm2));
+    // components: x=(0,1) y=(1,1) z=(1,0) w=(0,0) as (column offset, row offset)
+    const float4 g = tex2Dgather<float4>(tex, uc1, vc1, 0);
     const float top = fmaf(fu, g.z - g.w, g.w);
     const float bot = fmaf(fu, g.y - g.x, g.x);
     return fmaf(fv, bot - top, top);
@@ -237,8 +236,11 @@ __global__ void __launch_bounds__(32, MINB) ncc_score_pmvs(const PmvsArgs A, int
                 const double izd = 1.0 / Zv;
                 const double uc = (cv.fx * Xc + cv.cx * Zv) * izd, vc = (cv.fy * Yc + cv.cy * Zv) * izd;
                 const double ucf = floor(uc), vcf = floor(vc);
-                va.iu = (float)ucf; va.fu = (float)(uc - ucf);
-                va.iv = (float)vcf; va.fv = (float)(vc - vcf);
+                // integer parts carry the view's tile origin inside the atlas and the +1 that addresses the
+                // centre of the 2x2 gather footprint, so a tap coordinate is iu + floor(.) with no further adds
+                const float2 org = A.off[v];
+                va.iu = (float)ucf + org.x + 1.0f; va.fu = (float)(uc - ucf);
+                va.iv = (float)vcf + org.y + 1.0f; va.fv = (float)(vc - vcf);
                 va.Z0 = (float)Zv;
                 const float rx0 = cf.r[0] * ex[0] + cf.r[1] * ex[1] + cf.r[2] * ex[2];
                 const float rx1 = cf.r[3] * ex[0] + cf.r[4] * ex[1] + cf.r[5] * ex[2];
@@ -279,8 +281,8 @@ __global__ void __launch_bounds__(32, MINB) ncc_score_pmvs(const PmvsArgs A, int
                     float u0, v0, fu, fv;
                     bool front = true;
                     if (reduce_a) {
-                        u0 = (float)col + aj[q];
-                        v0 = (float)row + ak[q];
+                        u0 = (float)col + aj[q] + off.x + 1.0f;
+                        v0 = (float)row + ak[q] + off.y + 1.0f;
                         fu = fv = 0.0f;
                     } else {
                         const float z = fmaf(ak[q], q1.z, fmaf(aj[q], q1.y, q1.x));
