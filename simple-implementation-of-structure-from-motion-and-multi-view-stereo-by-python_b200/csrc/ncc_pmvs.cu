@@ -504,6 +504,13 @@ int mvs_pmvs_prepare(mvs_ctx* ctx, cudaStream_t s) {
         mvs_set_error("Mode B set-up: a %d x %d view does not fit a gather texture (limit %d x %d)", W, H, max_w, max_h);
         return MVS_ERR_ARG;
     }
+    if (const char* e = getenv("MVS_PMVS_MAX_TEX")) {       // test knob: a smaller limit forces several atlases
+        const int lim = atoi(e);
+        if (lim >= W && lim >= H) {
+            max_w = max_w < lim ? max_w : lim;
+            max_h = max_h < lim ? max_h : lim;
+        }
+    }
     const int fit_x = max_w / W, fit_y = max_h / H;
     const int tiles_x = V < fit_x ? V : fit_x;                         // tiles per atlas row
     const int rows_all = (V + tiles_x - 1) / tiles_x;                  // tile rows needed in total

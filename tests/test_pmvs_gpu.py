@@ -80,6 +80,19 @@ def test_pmvs_many_views(built_lib, V, mu):
     assert (ref >= 32).any() and want["count"][ref >= 32].max() >= 2
 
 
+def test_pmvs_several_atlases(built_lib, monkeypatch):
+    """256 views of 4K need three atlases; a small texture-size limit forces the same path on a small ring
+    (12 views of 320 x 240 in atlases of at most 2 x 2 tiles -> three atlases)."""
+    import mvs_b200
+    from oracle import mode_b
+    monkeypatch.setenv("MVS_PMVS_MAX_TEX", "700")
+    rgb, K, R, t, cams, gray, c, nrm, ref = _ring(n=1500)
+    want = mode_b.score(gray, cams, c, nrm, ref, 0.7, mu=5)
+    with mvs_b200.MvsContext(rgb, K, R, t, Rrt=cams.R) as ctx:
+        out = ctx.score_pmvs_host(c, nrm, ref, min_ncc=0.7, mu=5, want_ncc=True)
+    _check_against(out, want, len(K), 0.7)
+
+
 def test_pmvs_candidate_mask(built_lib):
     import mvs_b200
     from oracle import mode_b
