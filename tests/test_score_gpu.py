@@ -88,7 +88,14 @@ def test_other_window_sizes_against_oracle(golden, built_lib, wid):
                      0.55, wid=wid)
     with _ctx(d, built_lib) as ctx:
         out = ctx.score_host(d["c"], d["ref"], min_ncc=0.55, wid=wid, want_ncc=True)
+        # nine copies: >= 8192 hypotheses take the tile-ordered path, copies of one hypothesis share their loads
+        rep = 9
+        big = ctx.score_host(np.tile(d["c"], (rep, 1)), np.tile(d["ref"], rep), min_ncc=0.55, wid=wid, want_ncc=True)
     _compare(out, o["vis"], o["ncc"], o["avg"], V)
+    n = len(d["c"])
+    for k in ("vis_mask", "count", "avg", "xy", "ncc"):
+        assert np.array_equal(big[k].reshape((rep, n) + big[k].shape[1:]), np.broadcast_to(out[k], (rep,) + out[k].shape),
+                              equal_nan=True), k
 
 
 @pytest.mark.parametrize("V,H,W,N", [(48, 480, 640, 6000), (70, 120, 200, 6000), (33, 97, 131, 6000), (130, 120, 160, 6000),
