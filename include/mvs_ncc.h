@@ -301,6 +301,17 @@ int mvs_ncc_pairs(int device, int64_t M, int n, const uint8_t* a, const uint8_t*
 int mvs_profile_enable(mvs_ctx* ctx, int on);
 int mvs_profile_score_ms(mvs_ctx* ctx, float* mean_ms, int* n_kernels);
 
+/*
+ * Gather-ceiling probe (the measured L1/L2 gather ceiling that the roofline of the
+ * L2-resident configurations is reported against).  While on, the scoring launch of
+ * mvs_score_batch(MVS_MODE_REFEXACT) is replaced by a loads-only kernel that walks the ordered batch
+ * exactly as K1 does and issues exactly K1's loads (16-byte view quads of every window row and pixel
+ * group, reference-window words, map entries) with no arithmetic and no stores; the outputs of such a
+ * call are NOT written.  Timed through mvs_profile_enable / mvs_profile_score_ms like K1 itself.
+ * Replaces: nothing in the reference (measurement only).
+ */
+int mvs_profile_probe(mvs_ctx* ctx, int on);
+
 /* Number of kernels this library has launched on ctx since creation (for bench.py's
  * gpu_launches claim). */
 int64_t mvs_launch_count(const mvs_ctx* ctx);

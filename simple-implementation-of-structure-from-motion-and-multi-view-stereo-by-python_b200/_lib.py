@@ -28,6 +28,7 @@ SYMBOLS = {
     "mvs_select_best": (C.c_int, [_P, C.c_int64, C.c_int, _P, _P, C.c_int, _P, _P, _P]),
     "mvs_launch_count": (C.c_int64, [_P]),
     "mvs_profile_enable": (C.c_int, [_P, C.c_int]),
+    "mvs_profile_probe": (C.c_int, [_P, C.c_int]),
     "mvs_profile_score_ms": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "mvs_record_bytes": (C.c_int, [_P]),
     "mvs_cells_init": (C.c_int, [_P, C.c_int, _P]),

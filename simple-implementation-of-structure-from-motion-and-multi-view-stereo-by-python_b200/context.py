@@ -119,6 +119,10 @@ class MvsContext:
         """Bracket every scoring kernel with CUDA events on its launch stream."""
         _check(_lib.load().mvs_profile_enable(self._h, 1 if on else 0), "mvs_profile_enable")
 
+    def probe(self, on=True):
+        """Swap K1 for the loads-only gather-ceiling probe (measurement only; outputs are not written)."""
+        _check(_lib.load().mvs_profile_probe(self._h, 1 if on else 0), "mvs_profile_probe")
+
     def score_kernel_ms(self):
         """(mean ms, n) over the scoring kernels (K1 alone) launched since profile(True), at most
         the last 64; waits for them to finish."""

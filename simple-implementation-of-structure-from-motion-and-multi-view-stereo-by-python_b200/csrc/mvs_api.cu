@@ -314,6 +314,12 @@ extern "C" int mvs_profile_score_ms(mvs_ctx* ctx, float* mean_ms, int* n_kernels
     return MVS_OK;
 }
 
+extern "C" int mvs_profile_probe(mvs_ctx* ctx, int on) {
+    if (!ctx) { mvs_set_error("null context"); return MVS_ERR_ARG; }
+    ctx->probe_gather = on ? 1 : 0;
+    return MVS_OK;
+}
+
 extern "C" int64_t mvs_launch_count(const mvs_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }

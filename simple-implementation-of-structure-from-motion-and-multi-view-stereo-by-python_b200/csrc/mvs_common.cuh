@@ -61,6 +61,7 @@ struct mvs_ctx {
         bin_scan_bytes;
     // optional CUDA-event bracket around the scoring kernel (mvs_profile_enable)
     int profile;
+    int probe_gather;     // mvs_probe_gather: the scoring launch runs the loads-only ceiling probe instead of K1
     cudaEvent_t prof_ev[2 * MVS_PROF_RING];
     int64_t prof_n;       // scoring kernels bracketed since mvs_profile_enable(1)
     // Mode B texture path (ncc_pmvs.cu), created on the first Mode B call

@@ -497,6 +497,126 @@ __global__ void __launch_bounds__(256, MINB)
     }
 }
 
+
+// ---------------------------------------------------------------------------------
+// gather_probe: the measured CEILING of K1's memory side ("the builder must measure the
+// L2 gather ceiling with a micro-benchmark").  Same traversal of the ordered batch, same lane
+// mapping, same pairing of positions that share (row, pixel group), and exactly the loads K1
+// issues for a block -- the 16-byte view quads of every window row and pixel group, the
+// reference-window words, the two map entries per lane, ref / smap / vmap of the reference view --
+// but NO arithmetic: every loaded word is XOR-folded into one register so that the loads stay
+// live, and nothing is stored.  bench.py times it on the same inputs right after K1;
+// roofline.frac = probe time / K1 time.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t fold4(uint32_t acc, const uint4& w) {
+    return (acc ^ w.x ^ w.y) ^ (w.z ^ w.w);
+}
+
+template <int WID, int LPH, int NB, int GS>
+__device__ __forceinline__ uint32_t probe_block(const ScoreArgs& A, const uint32_t (&anchor)[NB], const int64_t (&h)[NB],
+                                                int lih) {
+    constexpr int K = 2 * WID + 1;
+    constexpr int NG = (K + 6) / 4;
+    const int64_t gstride = GS ? (int64_t)GS : A.gstride;
+    const int passes = (LPH == 32) ? (A.Q + 31) >> 5 : 1;
+    const int row = (int)(anchor[0] >> 16);
+    const int cg = ((int)(anchor[0] & 0xffffu) - WID) >> 2;
+    const uint8_t* base = A.gray4 + (int64_t)(row - WID) * A.rowpitch + (int64_t)cg * gstride;
+    uint32_t acc = 0u;
+    int64_t mi[NB];
+    bool need_last = false;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        const int col = (int)(anchor[b] & 0xffffu);
+        const int r = __ldg(A.ref + h[b]);
+        mi[b] = ((int64_t)row * A.W + col) * A.Vp;
+        acc ^= (uint32_t)__ldg(A.smap + mi[b] + r) ^ __ldg(A.vmap + mi[b] + r);
+        need_last |= group_mask((col - WID) & 3, K, NG - 1) != 0u;
+        // the reference-window words K1 stages in shared memory
+        for (int idx = lih; idx < K * NG; idx += LPH) {
+            const int rr = idx / NG, g = idx - rr * NG;
+            acc ^= __ldg(reinterpret_cast<const uint32_t*>(base + rr * A.rowpitch + g * gstride + 4 * r));
+        }
+    }
+    const uint32_t lastoff = need_last ? (uint32_t)((NG - 1) * gstride) : 0u;
+    for (int p = 0; p < passes; ++p) {
+        const int qq = p * LPH + lih;
+        const int qc = qq < A.Q ? qq : A.Q - 1;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const uint2 s2 = __ldg(reinterpret_cast<const uint2*>(A.smap + mi[b] + 4 * qc));
+            const uint4 v4 = __ldg(reinterpret_cast<const uint4*>(A.vmap + mi[b] + 4 * qc));
+            acc = fold4(acc ^ s2.x ^ s2.y, v4);
+        }
+        const uint8_t* prow = base + (int64_t)qc * 16;
+#pragma unroll
+        for (int rr = 0; rr < K; ++rr) {
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                const uint8_t* pw = (g == NG - 1) ? prow + lastoff : prow + g * gstride;
+                acc = fold4(acc, __ldg(reinterpret_cast<const uint4*>(pw)));
+            }
+            prow += A.rowpitch;
+        }
+    }
+    return acc;
+}
+
+template <int WID, int LPH, int GS, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+    gather_probe(const ScoreArgs A, int64_t N, const uint32_t* __restrict__ anchors, const uint2* __restrict__ entries,
+                 uint32_t* __restrict__ sink) {
+    constexpr int HPW = 32 / LPH;
+    constexpr int ITERS = MVS_K1_ITERS;
+    constexpr int CHUNK = 8 * HPW * 2 * ITERS;
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int sub = lane / LPH;
+    const int lih = lane % LPH;
+    uint32_t acc = 0u;
+    for (int64_t i0 = (int64_t)blockIdx.x * CHUNK; i0 < N; i0 += (int64_t)gridDim.x * CHUNK) {
+        for (int it = 0; it < ITERS; ++it) {
+            const int64_t i = i0 + 2 * ((it * 8 + wib) * HPW + sub);
+            if (i >= N) continue;
+            uint32_t a0, a1 = MVS_ANCHOR_INVALID;
+            int64_t h0 = i, h1 = i + 1;
+            if (entries) {
+                const uint2 e0 = __ldg(entries + i);
+                h0 = e0.x;
+                a0 = e0.y;
+                if (i + 1 < N) {
+                    const uint2 e1 = __ldg(entries + i + 1);
+                    h1 = e1.x;
+                    a1 = e1.y;
+                }
+            } else {
+                a0 = __ldg(anchors + i);
+                if (i + 1 < N) a1 = __ldg(anchors + i + 1);
+            }
+            const bool ok0 = a0 != MVS_ANCHOR_INVALID, ok1 = a1 != MVS_ANCHOR_INVALID;
+            const bool same = ok0 && ok1 && ((a0 >> 16) == (a1 >> 16)) &&
+                              ((((int)(a0 & 0xffffu) - WID) >> 2) == (((int)(a1 & 0xffffu) - WID) >> 2));
+            if (same) {
+                const uint32_t aa[2] = {a0, a1};
+                const int64_t hh[2] = {h0, h1};
+                acc ^= probe_block<WID, LPH, 2, GS>(A, aa, hh, lih);
+            } else {
+                if (ok0) {
+                    const uint32_t aa[1] = {a0};
+                    const int64_t hh[1] = {h0};
+                    acc ^= probe_block<WID, LPH, 1, GS>(A, aa, hh, lih);
+                }
+                if (ok1) {
+                    const uint32_t aa[1] = {a1};
+                    const int64_t hh[1] = {h1};
+                    acc ^= probe_block<WID, LPH, 1, GS>(A, aa, hh, lih);
+                }
+            }
+        }
+    }
+    if (acc == 0x9e3779b9u && sink) sink[blockIdx.x] = acc;       // keeps the loads live; practically never taken
+}
+
 #ifndef MVS_K1_MINB
 #define MVS_K1_MINB 4
 #endif
@@ -510,7 +630,10 @@ static int launch_gather_gs(mvs_ctx* ctx, const ScoreArgs& A, int64_t N, const u
     const int64_t want = (N + chunk - 1) / chunk;
     const int64_t cap = (int64_t)ctx->sm_count * MINB * 8;
     const int blocks = (int)(want < cap ? want : cap);
-    kern<<<blocks, 256, 0, s>>>(A, N, anchors, entries);
+    if (ctx->probe_gather)                                 // measurement hook: loads only, no results (mvs_probe_gather)
+        gather_probe<WID, LPH, GS, MINB><<<blocks, 256, 0, s>>>(A, N, anchors, entries, (uint32_t*)ctx->d_bin_hist);
+    else
+        kern<<<blocks, 256, 0, s>>>(A, N, anchors, entries);
     return MVS_OK;
 }
 
