@@ -43,6 +43,7 @@ WORKLOADS = {
                          desc="synthetic templeRing-shaped ring 47 views 640x480, depth x normal hypothesis sets (8 x 8)"),
     "temple47_mu7": dict(V=47, H=480, W=640, mode="B", mu=7, depths=8, normals=8,
                          desc="synthetic templeRing-shaped ring 47 views 640x480, depth x normal hypothesis sets (8 x 8)"),
+    "temple47_a": dict(V=47, H=480, W=640, mode="A", wid=5, desc="synthetic templeRing-shaped ring 47 views 640x480"),
     "ring128_1080p": dict(V=128, H=1080, W=1920, mode="A", wid=5, desc="synthetic ring 128 views 1920x1080"),
     "ring256_4k": dict(V=256, H=2160, W=3840, mode="A", wid=5, desc="synthetic ring 256 views 3840x2160"),
 }

@@ -498,6 +498,264 @@ __global__ void __launch_bounds__(256, MINB)
 }
 
 
+
+// ---------------------------------------------------------------------------------
+// K1 for 33..48 views (dinoRing's 48, the temple-shaped 47): "quad + pair" lanes.
+//
+// EIGHT lanes own a block of two hypotheses, four blocks per warp.  Lane l owns the view quad
+// 4l..4l+3 (one LDG.128 per window row and pixel group) AND the view pair 32+2l, 33+2l (one
+// LDG.64), i.e. six views: every lane is busy at 48 views (the 16-lane mapping idles a quarter of
+// them) and a warp instruction returns only bytes that are used -- 6 data-pipe wavefronts per four
+// blocks instead of 4 per two.  Control flow is WARP-UNIFORM: each lane group walks its own run of
+// PER consecutive positions of the ordered batch, pairing a position with its successor when both
+// read the same quads (same window row and first pixel group); a lone position is scored as a
+// block whose second member is a masked duplicate, a finished group idles on duplicates of its last
+// block.  All shuffles therefore use the full mask (no WARPSYNC/ENDCOLLECTIVE sequences around
+// partial-mask collectives) and stay inside their 8-lane segment.
+// ---------------------------------------------------------------------------------
+#ifndef MVS_K6_PER
+#define MVS_K6_PER 16
+#endif
+
+__device__ __forceinline__ uint32_t seg8_or(uint32_t v) {
+    v |= __shfl_xor_sync(FULL, v, 1);
+    v |= __shfl_xor_sync(FULL, v, 2);
+    v |= __shfl_xor_sync(FULL, v, 4);
+    return v;
+}
+
+template <int WID, int GS, int MINB, bool WANT_NCC>
+__global__ void __launch_bounds__(256, MINB)
+    ncc_score_gather6(const ScoreArgs A, int64_t N, const uint32_t* __restrict__ anchors, const uint2* __restrict__ entries) {
+    constexpr int K = 2 * WID + 1;
+    constexpr int NG = (K + 6) / 4;
+    constexpr int NPIX = K * K;
+    constexpr int PER = MVS_K6_PER;
+    constexpr int CHUNK = 32 * PER;                        // 8 warps x 4 lane groups x PER positions
+    __shared__ __align__(16) uint32_t s_ref[8][4][2][K][NG];
+
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int grp = lane >> 3;
+    const int lih = lane & 7;
+    uint32_t(*sref)[K][NG] = s_ref[wib][grp];
+    const int64_t gstride = GS ? (int64_t)GS : A.gstride;
+    const int Q2 = (A.Vp - 32) >> 1;                       // lanes that also own a view pair (1..8)
+    const int lp = lih < Q2 ? lih : Q2 - 1;                // lanes past the last pair shadow it (same L1 lines)
+    const double cn = (double)NPIX / (double)(NPIX - 1);
+    const double thr = A.thr;
+    // views this lane may score at all: inside V, and the pair only on lanes that own one
+    uint32_t lane_views = 0u;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (4 * lih + k < A.V) lane_views |= 1u << k;
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+        if (lih < Q2 && 32 + 2 * lih + k < A.V) lane_views |= 16u << k;
+
+    for (int64_t i0 = (int64_t)blockIdx.x * CHUNK; i0 < N; i0 += (int64_t)gridDim.x * CHUNK) {
+        int64_t pos = i0 + (int64_t)((wib * 4 + grp) * PER);
+        const int64_t end = (pos + PER < N) ? pos + PER : N;
+        while (__any_sync(FULL, pos < end)) {
+            // ---- this group's next block: position pos, paired with pos + 1 when both read the same quads
+            uint32_t a[2] = {MVS_ANCHOR_INVALID, MVS_ANCHOR_INVALID};
+            int64_t h[2] = {0, 0};
+            if (pos < end) {
+                if (entries) {
+                    const uint2 e0 = __ldg(entries + pos);
+                    h[0] = e0.x;
+                    a[0] = e0.y;
+                    if (pos + 1 < end) {
+                        const uint2 e1 = __ldg(entries + pos + 1);
+                        h[1] = e1.x;
+                        a[1] = e1.y;
+                    }
+                } else {
+                    h[0] = pos;
+                    a[0] = __ldg(anchors + pos);
+                    if (pos + 1 < end) {
+                        h[1] = pos + 1;
+                        a[1] = __ldg(anchors + pos + 1);
+                    }
+                }
+            }
+            bool live[2];
+            live[0] = a[0] != MVS_ANCHOR_INVALID;
+            live[1] = live[0] && a[1] != MVS_ANCHOR_INVALID && ((a[0] >> 16) == (a[1] >> 16)) &&
+                      ((((int)(a[0] & 0xffffu) - WID) >> 2) == (((int)(a[1] & 0xffffu) - WID) >> 2));
+            pos += live[1] ? 2 : 1;
+            if (!__any_sync(FULL, live[0])) continue;      // nothing to score in the whole warp (rejected hypotheses)
+            if (!live[0]) a[0] = ((uint32_t)WID << 16) | (uint32_t)(WID + 1);   // idle group: a window that is always inside
+            if (!live[1]) {
+                a[1] = a[0];
+                h[1] = h[0];
+            }
+
+            const int row = (int)(a[0] >> 16);
+            const int cg = ((int)(a[0] & 0xffffu) - WID) >> 2;
+            const uint8_t* base = A.gray4 + (int64_t)(row - WID) * A.rowpitch + (int64_t)cg * gstride;
+            int r[2], o[2], Sr[2];
+            int64_t mi[2];
+            double var_r[2], var_rs[2];
+            bool need_last = false;
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                const int col = (int)(a[b] & 0xffffu);
+                r[b] = live[0] ? __ldg(A.ref + h[b]) : 0;
+                o[b] = (col - WID) & 3;
+                mi[b] = ((int64_t)row * A.W + col) * A.Vp;
+                Sr[b] = (int)__ldg(A.smap + mi[b] + r[b]);
+                var_r[b] = (double)__ldg(A.vmap + mi[b] + r[b]);
+                var_rs[b] = var_r[b] * ((double)((NPIX - 1) * (NPIX - 1)) / (double)(NPIX * NPIX));
+                need_last |= group_mask(o[b], K, NG - 1) != 0u;
+            }
+            const uint32_t lastoff = need_last ? (uint32_t)((NG - 1) * gstride) : 0u;
+
+            // ---- reference windows: masked words to shared memory
+            __syncwarp();
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                if constexpr (NG == 4) {                   // a lane always stages the same pixel group
+                    const int g = lih & 3;
+                    const uint32_t mg = group_mask(o[b], K, g);
+                    const uint8_t* pr = base + g * gstride + 4 * r[b] + (lih >> 2) * A.rowpitch;
+#pragma unroll
+                    for (int rr0 = 0; rr0 < K; rr0 += 2) {
+                        const int rr = rr0 + (lih >> 2);
+                        if (rr < K) sref[b][rr][g] = __ldg(reinterpret_cast<const uint32_t*>(pr)) & mg;
+                        pr += 2 * A.rowpitch;
+                    }
+                } else {
+                    for (int idx = lih; idx < K * NG; idx += 8) {
+                        const int rr = idx / NG, g = idx - rr * NG;
+                        const uint32_t mg = group_mask(o[b], K, g);
+                        sref[b][rr][g] = __ldg(reinterpret_cast<const uint32_t*>(base + rr * A.rowpitch + g * gstride + 4 * r[b])) & mg;
+                    }
+                }
+            }
+            __syncwarp();
+
+            // ---- window sums of this lane's six views (maps) and the dot products
+            uint2 s4[2];
+            uint32_t s2[2];
+            uint4 v4[2];
+            uint2 v2[2];
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                s4[b] = __ldg(reinterpret_cast<const uint2*>(A.smap + mi[b] + 4 * lih));
+                v4[b] = __ldg(reinterpret_cast<const uint4*>(A.vmap + mi[b] + 4 * lih));
+                s2[b] = __ldg(reinterpret_cast<const uint32_t*>(A.smap + mi[b] + 32 + 2 * lp));
+                v2[b] = __ldg(reinterpret_cast<const uint2*>(A.vmap + mi[b] + 32 + 2 * lp));
+            }
+            int SAB[2][6];
+#pragma unroll
+            for (int b = 0; b < 2; ++b)
+#pragma unroll
+                for (int k = 0; k < 6; ++k) SAB[b][k] = 0;
+            const uint8_t* p4 = base + 16 * lih;
+            const uint8_t* p2 = base + 128 + 8 * lp;
+#pragma unroll
+            for (int rr = 0; rr < K; ++rr) {
+                uint32_t rw[2][NG];
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    if constexpr (NG == 4) {
+                        const uint4 t4 = *reinterpret_cast<const uint4*>(&sref[b][rr][0]);
+                        rw[b][0] = t4.x; rw[b][1] = t4.y; rw[b][2] = t4.z; rw[b][3] = t4.w;
+                    } else {
+#pragma unroll
+                        for (int g = 0; g < NG; ++g) rw[b][g] = sref[b][rr][g];
+                    }
+                }
+#pragma unroll
+                for (int g = 0; g < NG; ++g) {
+                    const uint32_t off = (g == NG - 1) ? lastoff : (uint32_t)(g * gstride);
+                    const uint4 w4 = __ldg(reinterpret_cast<const uint4*>(p4 + off));
+                    const uint2 w2 = __ldg(reinterpret_cast<const uint2*>(p2 + off));
+#pragma unroll
+                    for (int b = 0; b < 2; ++b) {
+                        SAB[b][0] = dp4a_u(w4.x, rw[b][g], SAB[b][0]);
+                        SAB[b][1] = dp4a_u(w4.y, rw[b][g], SAB[b][1]);
+                        SAB[b][2] = dp4a_u(w4.z, rw[b][g], SAB[b][2]);
+                        SAB[b][3] = dp4a_u(w4.w, rw[b][g], SAB[b][3]);
+                        SAB[b][4] = dp4a_u(w2.x, rw[b][g], SAB[b][4]);
+                        SAB[b][5] = dp4a_u(w2.y, rw[b][g], SAB[b][5]);
+                    }
+                }
+                p4 += A.rowpitch;
+                p2 += A.rowpitch;
+            }
+
+            // ---- this lane finishes its own six views of both hypotheses
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                const int Sv[6] = {(int)(s4[b].x & 0xffffu), (int)(s4[b].x >> 16), (int)(s4[b].y & 0xffffu), (int)(s4[b].y >> 16),
+                                   (int)(s2[b] & 0xffffu),   (int)(s2[b] >> 16)};
+                const uint32_t var[6] = {v4[b].x, v4[b].y, v4[b].z, v4[b].w, v2[b].x, v2[b].y};
+                uint32_t okmask = (live[b] && var_r[b] != 0.0) ? lane_views : 0u;
+                if ((r[b] >> 2) == lih) okmask &= ~(1u << (r[b] & 3));                       // the reference view itself
+                if (r[b] >= 32 && ((r[b] - 32) >> 1) == lih) okmask &= ~(16u << (r[b] & 1));
+                auto numerator = [&](int k) {
+                    return (WID <= 5) ? s32_to_double(NPIX * SAB[b][k] - Sv[k] * Sr[b])
+                                      : (double)((long long)NPIX * SAB[b][k] - (long long)Sv[k] * Sr[b]);
+                };
+                uint32_t near = 0u, bits = 0u;
+                double acc = 0.0;
+                float dump[6];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    const double val = ncc_fast(numerator(k), u32_to_double(var[k]), var_rs[b]);
+                    if (var[k] == 0u) okmask &= ~(1u << k);
+                    const bool vis = ((okmask >> k) & 1u) && (val > thr);
+                    acc += vis ? val : 0.0;
+                    bits |= vis ? (1u << k) : 0u;
+                    if (fabs(val - thr) < 1e-9) near |= 1u << k;
+                    if constexpr (WANT_NCC) dump[k] = (float)val;
+                }
+                near &= okmask;
+                if (__builtin_expect(near != 0u, 0)) {
+                    // rare: a value within 1e-9 of the threshold is redone with the correctly rounded sqrt and
+                    // division and the provisional decision / sum contribution replaced
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) {
+                        if (!((near >> k) & 1u)) continue;
+                        const double num = numerator(k), vd = u32_to_double(var[k]);
+                        const double fast = ncc_fast(num, vd, var_rs[b]);
+                        const double exact = ncc_exact(num, vd, var_r[b], cn);
+                        if ((bits >> k) & 1u) acc -= fast;
+                        bits &= ~(1u << k);
+                        if (exact > thr) {
+                            acc += exact;
+                            bits |= 1u << k;
+                        }
+                        if constexpr (WANT_NCC) dump[k] = (float)exact;
+                    }
+                }
+                if constexpr (WANT_NCC) {
+                    if (live[b]) {
+#pragma unroll
+                        for (int k = 0; k < 6; ++k) {
+                            const int v = k < 4 ? 4 * lih + k : 32 + 2 * lih + (k - 4);
+                            if ((lane_views >> k) & 1u) A.ncc_out[h[b] * A.V + v] = ((okmask >> k) & 1u) ? dump[k] : nanf("");
+                        }
+                    }
+                }
+                // visible mask: bits 4l..4l+3 of the low word, bits 2l, 2l+1 of the high word
+                const uint32_t lo = seg8_or((bits & 15u) << (4 * lih));
+                const uint32_t hi = seg8_or((bits >> 4) << (2 * lih));
+#pragma unroll
+                for (int sft = 4; sft > 0; sft >>= 1) acc += __shfl_xor_sync(FULL, acc, sft);
+                const int count = __popc(lo) + __popc(hi);
+                if (live[b] && lih == 0) {
+                    reinterpret_cast<uint2*>(A.vis_out)[h[b]] = make_uint2(lo, hi);
+                    A.count_out[h[b]] = count;
+                    if (A.avg_out) A.avg_out[h[b]] = count > 0 ? acc / (double)count : 0.0;
+                }
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------
 // gather_probe: the measured CEILING of K1's memory side ("the builder must measure the
 // L2 gather ceiling with a micro-benchmark").  Same traversal of the ordered batch, same lane
@@ -617,6 +875,130 @@ __global__ void __launch_bounds__(256, MINB)
     if (acc == 0x9e3779b9u && sink) sink[blockIdx.x] = acc;       // keeps the loads live; practically never taken
 }
 
+
+// gather_probe6: the loads of ncc_score_gather6 (same walk, same pairing, same addresses), no arithmetic.
+template <int WID, int GS, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+    gather_probe6(const ScoreArgs A, int64_t N, const uint32_t* __restrict__ anchors, const uint2* __restrict__ entries,
+                  uint32_t* __restrict__ sink) {
+    constexpr int K = 2 * WID + 1;
+    constexpr int NG = (K + 6) / 4;
+    constexpr int PER = MVS_K6_PER;
+    constexpr int CHUNK = 32 * PER;
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int grp = lane >> 3;
+    const int lih = lane & 7;
+    const int64_t gstride = GS ? (int64_t)GS : A.gstride;
+    const int Q2 = (A.Vp - 32) >> 1;
+    const int lp = lih < Q2 ? lih : Q2 - 1;
+    uint32_t acc = 0u;
+    for (int64_t i0 = (int64_t)blockIdx.x * CHUNK; i0 < N; i0 += (int64_t)gridDim.x * CHUNK) {
+        int64_t pos = i0 + (int64_t)((wib * 4 + grp) * PER);
+        const int64_t end = (pos + PER < N) ? pos + PER : N;
+        while (__any_sync(FULL, pos < end)) {
+            uint32_t a[2] = {MVS_ANCHOR_INVALID, MVS_ANCHOR_INVALID};
+            int64_t h[2] = {0, 0};
+            if (pos < end) {
+                if (entries) {
+                    const uint2 e0 = __ldg(entries + pos);
+                    h[0] = e0.x;
+                    a[0] = e0.y;
+                    if (pos + 1 < end) {
+                        const uint2 e1 = __ldg(entries + pos + 1);
+                        h[1] = e1.x;
+                        a[1] = e1.y;
+                    }
+                } else {
+                    h[0] = pos;
+                    a[0] = __ldg(anchors + pos);
+                    if (pos + 1 < end) {
+                        h[1] = pos + 1;
+                        a[1] = __ldg(anchors + pos + 1);
+                    }
+                }
+            }
+            bool live[2];
+            live[0] = a[0] != MVS_ANCHOR_INVALID;
+            live[1] = live[0] && a[1] != MVS_ANCHOR_INVALID && ((a[0] >> 16) == (a[1] >> 16)) &&
+                      ((((int)(a[0] & 0xffffu) - WID) >> 2) == (((int)(a[1] & 0xffffu) - WID) >> 2));
+            pos += live[1] ? 2 : 1;
+            if (!__any_sync(FULL, live[0])) continue;
+            if (!live[0]) a[0] = ((uint32_t)WID << 16) | (uint32_t)(WID + 1);
+            if (!live[1]) {
+                a[1] = a[0];
+                h[1] = h[0];
+            }
+            const int row = (int)(a[0] >> 16);
+            const int cg = ((int)(a[0] & 0xffffu) - WID) >> 2;
+            const uint8_t* base = A.gray4 + (int64_t)(row - WID) * A.rowpitch + (int64_t)cg * gstride;
+            bool need_last = false;
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                const int col = (int)(a[b] & 0xffffu);
+                const int r = live[0] ? __ldg(A.ref + h[b]) : 0;
+                const int64_t mi = ((int64_t)row * A.W + col) * A.Vp;
+                acc ^= (uint32_t)__ldg(A.smap + mi + r) ^ __ldg(A.vmap + mi + r);
+                need_last |= group_mask((col - WID) & 3, K, NG - 1) != 0u;
+                for (int idx = lih; idx < K * NG; idx += 8) {
+                    const int rr = idx / NG, g = idx - rr * NG;
+                    acc ^= __ldg(reinterpret_cast<const uint32_t*>(base + rr * A.rowpitch + g * gstride + 4 * r));
+                }
+                const uint2 s4 = __ldg(reinterpret_cast<const uint2*>(A.smap + mi + 4 * lih));
+                const uint4 v4 = __ldg(reinterpret_cast<const uint4*>(A.vmap + mi + 4 * lih));
+                const uint32_t s2 = __ldg(reinterpret_cast<const uint32_t*>(A.smap + mi + 32 + 2 * lp));
+                const uint2 v2 = __ldg(reinterpret_cast<const uint2*>(A.vmap + mi + 32 + 2 * lp));
+                acc = fold4(acc ^ s4.x ^ s4.y ^ s2 ^ v2.x ^ v2.y, v4);
+            }
+            const uint32_t lastoff = need_last ? (uint32_t)((NG - 1) * gstride) : 0u;
+            const uint8_t* p4 = base + 16 * lih;
+            const uint8_t* p2 = base + 128 + 8 * lp;
+#pragma unroll
+            for (int rr = 0; rr < K; ++rr) {
+#pragma unroll
+                for (int g = 0; g < NG; ++g) {
+                    const uint32_t off = (g == NG - 1) ? lastoff : (uint32_t)(g * gstride);
+                    const uint2 w2 = __ldg(reinterpret_cast<const uint2*>(p2 + off));
+                    acc = fold4(acc ^ w2.x ^ w2.y, __ldg(reinterpret_cast<const uint4*>(p4 + off)));
+                }
+                p4 += A.rowpitch;
+                p2 += A.rowpitch;
+            }
+        }
+    }
+    if (acc == 0x9e3779b9u && sink) sink[blockIdx.x] = acc;
+}
+
+#ifndef MVS_K6_MINB
+#define MVS_K6_MINB 3
+#endif
+
+template <int WID, int GS, int MINB = MVS_K6_MINB>
+static int launch_gather6(mvs_ctx* ctx, const ScoreArgs& A, int64_t N, const uint32_t* anchors, const uint2* entries,
+                          cudaStream_t s) {
+    const int64_t chunk = 32 * MVS_K6_PER;
+    const int64_t want = (N + chunk - 1) / chunk;
+    const int64_t cap = (int64_t)ctx->sm_count * MINB * 8;
+    const int blocks = (int)(want < cap ? want : cap);
+    if (ctx->probe_gather)
+        gather_probe6<WID, GS, MINB><<<blocks, 256, 0, s>>>(A, N, anchors, entries, (uint32_t*)ctx->d_bin_hist);
+    else if (A.ncc_out)
+        ncc_score_gather6<WID, GS, MINB, true><<<blocks, 256, 0, s>>>(A, N, anchors, entries);
+    else
+        ncc_score_gather6<WID, GS, MINB, false><<<blocks, 256, 0, s>>>(A, N, anchors, entries);
+    return MVS_OK;
+}
+
+// MVS_K1_LEGACY=1: the 16-lane mapping for 33..48 views (kept for comparison)
+static int k1_legacy() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("MVS_K1_LEGACY");
+        v = e ? atoi(e) : 0;
+    }
+    return v;
+}
+
 #ifndef MVS_K1_MINB
 #define MVS_K1_MINB 4
 #endif
@@ -653,6 +1035,11 @@ static int launch_gather(mvs_ctx* ctx, const ScoreArgs& A, int64_t N, const uint
     const int Q = ctx->Q;
     if (Q <= 4) return launch_gather_gs<WID, 4, 0>(ctx, A, N, anchors, entries, s);
     if (Q <= 8) return launch_gather_gs<WID, 8, 0>(ctx, A, N, anchors, entries, s);
+    // 33..48 views: eight lanes per block, six views per lane (needs a window that fits the image for its idle groups)
+    if (Q > 8 && Q <= 12 && !k1_legacy() && ctx->H >= 2 * WID + 2 && ctx->W >= 2 * WID + 3) {
+        if (WID == 5 && Q == 12) return launch_gather6<5, 192>(ctx, A, N, anchors, entries, s);
+        return launch_gather6<WID, 0>(ctx, A, N, anchors, entries, s);
+    }
     if (Q <= 16) {
         // the reference's own configuration (wid 5, dinoRing's 48 views): group stride as an immediate
         if (WID == 5 && Q == 12) {
