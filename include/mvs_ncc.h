@@ -236,6 +236,39 @@ int mvs_cells_download(mvs_ctx* ctx, uint8_t* table_host);
 int mvs_cells_fill(mvs_ctx* ctx, const void* records, int64_t n, void* stream);
 
 /*
+ * CellTable.filter_out_outlier (MVS2.py:132-158; shipped by the reference but disabled as "very very slow",
+ * MVS2.py:280-281) for n patch records in INSERTION order (seeds first, then the expansion's patches in
+ * commit order): removed[i] = 1 for every patch the reference's scan would delete from its Q lists.  One
+ * thread per cell position walks the views in ascending order, exactly the reference's dependency (see
+ * csrc/filter.cu).  A non-vacant cell with an empty list (the reference raises ZeroDivisionError there) is
+ * skipped and counted.  The cell table itself is not modified (the reference does not modify it either).
+ *   records DEVICE, removed DEVICE [n] uint8, counts_host HOST [2] = {patches removed, empty non-vacant cells}
+ * Synchronises `stream`.
+ */
+int mvs_cells_filter(mvs_ctx* ctx, const void* records, int64_t n, uint8_t* removed, int64_t* counts_host, void* stream);
+
+/*
+ * cv2.triangulatePoints (utils.py:238-239) for n correspondences: x in view_a / view_b [n,2], projection
+ * matrices P [V,12] = K [R|t] (utils.py:234-236) -> homogeneous X4 [n,4].  HOST pointers; synchronous.
+ * OpenCV's algorithm (4x4 DLT system, one-sided Jacobi SVD) restated in fp64 on the device.
+ */
+int mvs_triangulate(mvs_ctx* ctx, int64_t n, const int32_t* view_a, const int32_t* view_b, const double* xa, const double* xb,
+                    const double* P, double* X4);
+
+/*
+ * Seed-patch stage (MVS2.py:208-260) for SfM tracks given as a flat observation list: track t owns
+ * obs[offsets[t] .. offsets[t+1]) rows of (view, x, y); its first observation is the reference, every
+ * further one is triangulated against it, all candidates are scored in one batch at `min_ncc` (0.4,
+ * MVS2.py:255) and the nearest candidate with >= bound visible views wins (heap key MVS2.py:14).  The
+ * winners become patch records in track order (index = candidate number, i.e. observation index minus
+ * (track + 1)); when a cell table is initialised their cells are filled (MVS2.py:258-259).
+ *   offsets HOST [n_tracks+1], obs HOST [n_obs,3], P HOST [V,12]; seeds DEVICE (capacity n_tracks records);
+ *   n_seeds HOST.  Synchronises `stream`.
+ */
+int mvs_seed_stage(mvs_ctx* ctx, int64_t n_tracks, const int64_t* offsets, const double* obs, const double* P, double min_ncc,
+                   int wid, int bound, void* seeds, int64_t* n_seeds, void* stream);
+
+/*
  * One synchronous expansion round, phase 1: candidate generation.
  * Replaces: patch_expansion's candidate loop (MVS2.py:328-361) for a whole frontier.
  * For every frontier patch f, every view v in its visible set and every diagonal
@@ -276,6 +309,76 @@ int mvs_round_score_p2p(mvs_ctx* ctx, const void* frontier, int64_t begin, int64
  * write them as the next frontier.  All pointers DEVICE pointers.
  */
 int mvs_round_commit(mvs_ctx* ctx, const void* records, int64_t n, void* next_frontier, int64_t* n_next, void* stream);
+
+/*
+ * Minimal wire between the GPUs of one box (exchange.cu).  In a round every GPU holds the same candidate
+ * list and scores its shard; a peer only lacks, per candidate, whether it passed, its visible set and its
+ * mean NCC.  A shard's wire is: header {int64 kept, int64 n}, one {u32 bits, u32 prefix} word per 32
+ * candidates, and {f64 avg, u64 vis[ceil(V/64)]} per PASSED candidate in candidate order.  An inbox holds
+ * two parity halves (double buffering: one barrier per round) of `world` regions of `capacity` candidates.
+ * Replaces: MVS_WIRE_COMPACT records for rounds (they also carried c, ref, px, slot -- resident on every GPU).
+ * The reference has no counterpart (single process).
+ */
+int64_t mvs_exchange_bytes(const mvs_ctx* ctx, int world, int64_t capacity);
+
+/*
+ * Publish the accept decisions of N scored hypotheses (count >= bound && gate) into region `rank` of the
+ * `parity` half of EVERY GPU's inbox (peer-mapped DEVICE pointers, HOST array of `world` entries; entry
+ * `rank` is this GPU's own inbox).  Plain stores over NVLink from inside the compaction kernels; follow with
+ * mvs_p2p_barrier before any GPU reads its inbox.  All data pointers DEVICE; enqueued on `stream`.
+ * Replaces: the accept branch of MVS2.py:369,401-403 + the per-round all-gather of SURVEY 8(e).
+ */
+int mvs_publish_accepted(mvs_ctx* ctx, int64_t N, const uint64_t* vis_mask, const double* avg, const int32_t* count,
+                         const uint8_t* gate, int bound, void* const* peer_inbox, int rank, int world, int64_t capacity,
+                         int parity, void* stream);
+
+/*
+ * Device-side barrier across the GPUs of the box: one tiny kernel, no host round trip, capturable in a
+ * CUDA graph.  peer_flags: HOST array of `world` DEVICE pointers, entry g = GPU g's array of `world`
+ * uint64 flags (zero-initialised by the caller before the first barrier) as mapped into this process.
+ * Every context must call it the same number of times.  A rank that waits ~4 s for a peer gives up and
+ * raises a sticky error that mvs_p2p_barrier_failed reports (it never hangs the GPU).
+ */
+int mvs_p2p_barrier(mvs_ctx* ctx, void* const* peer_flags, int rank, int world, void* stream);
+int mvs_p2p_barrier_failed(mvs_ctx* ctx, void* stream);
+
+/*
+ * The whole expansion in ONE call (all rounds; one host synchronisation per round, no Python between
+ * rounds).  Replaces: the while-loop of patch_expansion (MVS2.py:321-404) restructured into synchronous
+ * rounds (DESIGN.md "Rounds"): per round mvs_round_generate -> score this GPU's shard + accept gate ->
+ * mvs_publish_accepted -> [mvs_p2p_barrier] -> commit from the wire.  With world > 1 every GPU runs the
+ * same call on the same seeds and cell table; results do not depend on `world`.
+ */
+typedef struct mvs_expand_params {
+    double min_ncc;          /* MIN_NCC of MVS2.py:362 (0.7) */
+    double scale;            /* args.scale of MVS2.py:369 */
+    int32_t wid;             /* half window (5) */
+    int32_t bound;           /* visible_lower_bound (MVS2.py:200-203) */
+    int64_t max_rounds;      /* < 0: unlimited */
+    int64_t max_iterations;  /* patches EXPANDED, the reference's `iteration < 100000` (MVS2.py:321); < 0: unlimited */
+    int64_t max_patches;     /* stop after the round that reaches this many accepted patches; < 0: unlimited */
+    int32_t rank, world;     /* this GPU's shard; world == 1: no exchange */
+    void* const* peer_inbox; /* world > 1: see mvs_publish_accepted */
+    void* const* peer_flags; /* world > 1: see mvs_p2p_barrier */
+    int64_t capacity;        /* world > 1: candidates per inbox region; a round needs ceil(M / world) <= capacity */
+    int32_t timing;          /* != 0: CUDA events around every round -> mvs_round_stat.ms */
+    int32_t reserved;
+} mvs_expand_params;
+
+typedef struct mvs_round_stat {
+    int64_t frontier, candidates, passed, accepted;
+    float ms;
+    int32_t reserved;
+} mvs_round_stat;
+
+/*   seeds      DEVICE pointer to n_seeds patch records (already filled into the cell table)
+ *   stats      HOST array of max_stats entries (may be NULL); n_rounds, n_patches: HOST
+ * The accepted patches of all rounds stay in the context, in commit order (= round order, slot order
+ * inside a round); fetch them with mvs_expand_result. */
+int mvs_expand_run(mvs_ctx* ctx, const void* seeds, int64_t n_seeds, const mvs_expand_params* params, mvs_round_stat* stats,
+                   int max_stats, int* n_rounds, int64_t* n_patches, void* stream);
+/* Copy accepted records [offset, offset + n) of the last mvs_expand_run to `records` (HOST, or DEVICE with on_device). */
+int mvs_expand_result(mvs_ctx* ctx, void* records, int64_t offset, int64_t n, int on_device, void* stream);
 
 /* Debug/parity access to the candidates of the last mvs_round_generate: any pointer may be
  * NULL; HOST pointers.  slot [M] int64, parent [M] int64, c [M,3], nrm [M,3], ref [M] int32. */

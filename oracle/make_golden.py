@@ -17,6 +17,8 @@ Fixtures:
                        (0.4 at MVS2.py:255, 0.7 at MVS2.py:362) + every ctNcc value.
   synth5_scores.npz    5 synthetic 40x56 views (noise, flat areas, gradients) with
                        hypotheses placed on every side of the bounds rule.
+  filter12.npz         CellTable.filter_out_outlier (MVS2.py:132-158) run by the reference on real
+                       reference patches + seeded low-score clones: removed flags, surviving Q lists.
   dino12_expansion.npz event log of the reference's patch_expansion
                        (MVS2.py:308-404) run for a capped number of iterations from
                        seeded initial patches: parents, candidates, scores, accepts.
@@ -326,6 +328,19 @@ def make_full(ref_mvs2, imgs, par_text, n=1024):
     os.makedirs(os.path.join(HERE, "_ref"), exist_ok=True)
     np.savez_compressed(os.path.join(HERE, "_ref", "dinoRing_full.npz"), rgb=np.stack(imgs), K=K, R=R, t=t,
                         Rrt=cv_roundtrip(R), c=c, ref=ref, thresholds=np.array([0.4, 0.7]), **out)
+    export_dataset()
+
+
+def export_dataset():
+    """data/_ref/dinoRing.npz (git-ignored, travels with the repo snapshot): the INPUTS of BASELINE config 2 --
+    the reference's dinoRing images + cameras and one instance of its SfM tracks -- on a neutral path, so that
+    bench.py's product arm never reads under oracle/.  No reference outputs in it."""
+    full = np.load(os.path.join(HERE, "_ref", "dinoRing_full.npz"))
+    tr = np.load(os.path.join(GOLD, "dino_tracks.npz"))
+    dst = os.path.join(os.path.dirname(HERE), "data", "_ref")
+    os.makedirs(dst, exist_ok=True)
+    np.savez_compressed(os.path.join(dst, "dinoRing.npz"), rgb=full["rgb"], K=full["K"], R=full["R"], t=full["t"],
+                        Rrt=full["Rrt"], obs=tr["obs"], offsets=tr["offsets"])
 
 
 def make_tracks():
@@ -378,11 +393,76 @@ def make_tracks():
     return len(offs) - 1, len(obs), len(seeds)
 
 
+def make_filter(ref_mvs2, seed=7):
+    """filter12.npz: CellTable.filter_out_outlier (MVS2.py:132-158) run by the reference itself on a Q table
+    built from the patches of dino12_expansion.npz (real reference patches) plus seeded clones with lowered
+    scores / displaced centres, so that removals, near-misses and order dependence across views all occur."""
+    g = np.load(os.path.join(GOLD, "dino12_expansion.npz"))
+    rng = np.random.default_rng(seed)
+    c, n, avg, vis, xy = [g[k].copy() for k in ("c", "n", "avg", "vis", "xy")]
+    keep = vis.sum(1) > 0
+    c, n, avg, vis, xy = c[keep], n[keep], avg[keep], vis[keep], xy[keep]
+    base = len(c)
+    extra = dict(c=[], n=[], avg=[], vis=[], xy=[])
+    for k in range(base):
+        r = rng.random()
+        if r > 0.45:
+            continue
+        for _ in range(int(rng.integers(1, 4))):
+            kind = rng.integers(0, 4)
+            cc = c[k] + (0.5 if kind != 1 else 0.01) * n[k] * (1 if rng.random() < 0.5 else -1)   # kind 1: a neighbour
+            a = float(rng.uniform(0.0, 0.2)) if kind != 2 else float(rng.uniform(0.5, 0.9))         # kind 2: scores too well
+            vv = vis[k].copy()
+            if kind == 3:                                                                           # partial overlap of the views
+                on = np.nonzero(vv)[0]
+                vv[on[rng.random(len(on)) < 0.4]] = False
+                if not vv.any():
+                    vv[on[0]] = True
+            extra["c"].append(cc); extra["n"].append(n[k]); extra["avg"].append(a); extra["vis"].append(vv); extra["xy"].append(xy[k])
+    c = np.concatenate([c, np.array(extra["c"])]); n = np.concatenate([n, np.array(extra["n"])])
+    avg = np.concatenate([avg, np.array(extra["avg"])]); vis = np.concatenate([vis, np.array(extra["vis"])])
+    xy = np.concatenate([xy, np.array(extra["xy"])])
+    order = rng.permutation(len(c))                           # insertion order is not "real first"
+    c, n, avg, vis, xy = c[order], n[order], avg[order], vis[order], xy[order]
+    V = vis.shape[1]
+    H, W = CROP[1] - CROP[0], CROP[3] - CROP[2]
+    cell_size = int(g["cell_size"])
+    imgs = [np.zeros((H, W, 3), np.uint8) for _ in range(V)]
+    cells = ref_mvs2.CellTable(imgs, cell_size=cell_size)
+    patches = []
+    for k in range(len(c)):
+        p = ref_mvs2.MyPatch(c[k], n[k], 0, [[int(v), float(xy[k, 0]), float(xy[k, 1])] for v in np.nonzero(vis[k])[0]], None, None)
+        p.avg_ncc_score = float(avg[k])
+        patches.append(p)
+        for hit in p.V:
+            cells.fill_with_point(hit[0], hit[1], hit[2], p)                     # MVS2.py:98-107
+    table = np.stack([np.asarray(t) for t in cells.table])
+    with contextlib.redirect_stdout(io.StringIO()):
+        cells.filter_out_outlier()
+    alive = set()
+    for lst in cells.Q_table.values():
+        alive.update(id(p) for p in lst)
+    removed = np.array([id(p) not in alive for p in patches])
+    # the surviving Q lists, flattened, for the restatement's own check
+    index = {id(p): k for k, p in enumerate(patches)}
+    keys, members = [], []
+    for key in sorted(k for k, lst in cells.Q_table.items() if lst):
+        keys.append(key)
+        members.append(sorted(set(index[id(p)] for p in cells.Q_table[key])))
+    np.savez_compressed(os.path.join(GOLD, "filter12.npz"), c=c, n=n, avg=avg, vis=vis, xy=xy, table=table,
+                        cell_size=np.int64(cell_size), removed=removed,
+                        q_keys=np.array(keys, dtype=np.int32),
+                        q_offsets=np.cumsum([0] + [len(m) for m in members]).astype(np.int64),
+                        q_members=np.concatenate(members).astype(np.int32))
+    return len(c), int(removed.sum()), len(keys)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--tracks", action="store_true", help="only (re)record the SfM tracks of dinoRing")
     ap.add_argument("--full", action="store_true")
     ap.add_argument("--full-n", type=int, default=1024)
+    ap.add_argument("--filter", action="store_true", help="only (re)record the filter_out_outlier fixture")
     ap.add_argument("--only-full", action="store_true", help="leave the committed fixtures untouched")
     a = ap.parse_args()
     if not os.path.isdir(REF):
@@ -393,6 +473,9 @@ def main():
         return
     ref_mvs2, ref_main = import_reference()
     imgs, par_text = load_dino(ref_main)
+    if a.filter:
+        print("filter12: %d patches, %d removed by the reference, %d non-empty Q lists left" % make_filter(ref_mvs2))
+        return
     if a.only_full:
         make_full(ref_mvs2, imgs, par_text, a.full_n)
         print("oracle/_ref/dinoRing_full.npz done")

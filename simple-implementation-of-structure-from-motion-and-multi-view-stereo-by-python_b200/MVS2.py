@@ -62,20 +62,45 @@ def _roundtrip(R):
     return np.stack([cv2.Rodrigues(cv2.Rodrigues(r)[0])[0] for r in R])
 
 
-_CTX = {"key": None, "ctx": None}
+_CTX = {"key": None, "ctx": None, "imgs": None}
+
+
+def _fingerprint(imgs):
+    """Cheap content fingerprint of the image list: a strided sample of every image plus the first and last
+    rows.  Part of the context key, so that a NEW list that happens to reuse the id() of a freed one, or
+    pixels edited in place, do not silently score against a stale GPU stack."""
+    import zlib
+    h = 0
+    for im in imgs:
+        a = np.asarray(im)
+        flat = a.reshape(-1)
+        h = zlib.crc32(np.ascontiguousarray(flat[:: max(1, flat.size // 4096)]).tobytes(), h)
+        h = zlib.crc32(np.ascontiguousarray(a[0]).tobytes(), h)
+        h = zlib.crc32(np.ascontiguousarray(a[-1]).tobytes(), h)
+    return h
 
 
 def _context(imgs, par_K, par_r, par_t):
-    """The image stack and cameras live on the GPU once per (image list, cameras)."""
+    """The image stack and cameras live on the GPU once per (image list, cameras).  The cache keeps a
+    strong reference to the list (its id() cannot be recycled while cached) and keys on a content
+    fingerprint; MVS_CTX_STRICT=1 fingerprints every pixel."""
     V = len(imgs)
     K, R, t = _stack_pars(par_K, par_r, par_t, V)
-    key = (id(imgs), V, imgs[0].shape, K.tobytes(), R.tobytes(), t.tobytes())
+    if os.environ.get("MVS_CTX_STRICT"):
+        import zlib
+        fp = 0
+        for im in imgs:
+            fp = zlib.crc32(np.ascontiguousarray(im).tobytes(), fp)
+    else:
+        fp = _fingerprint(imgs)
+    key = (id(imgs), V, imgs[0].shape, fp, K.tobytes(), R.tobytes(), t.tobytes())
     if _CTX["key"] != key:
         if _CTX["ctx"] is not None:
             _CTX["ctx"].close()
         device = int(os.environ.get("MVS_DEVICE", os.environ.get("LOCAL_RANK", "0")))
         _CTX["ctx"] = MvsContext(imgs, K, R, t, Rrt=_roundtrip(R), device=device)
         _CTX["key"] = key
+        _CTX["imgs"] = imgs
     return _CTX["ctx"]
 
 
@@ -155,16 +180,47 @@ class MyPatch(object):
 
 
 class CellTable(object):
-    """MVS2.py:80-173: per-view vacancy grids (host mirror; the expansion keeps its own copy
-    in HBM and writes it back here) and the cell -> patches map."""
+    """MVS2.py:80-173: per-view vacancy grids (host mirror; the expansion keeps its own copy in HBM and
+    writes it back here) and the cell -> patches map.  The patches the device expansion accepts arrive as
+    record ARRAYS; ``Q_table`` materialises them into MyPatch objects only when somebody reads it, and
+    ``reconstruct_from_Q`` / ``filter_out_outlier`` work on the arrays directly."""
 
     def __init__(self, imgs, cell_size=4.0):
         self.table = []
-        self.Q_table = defaultdict(list)
+        self._Q = defaultdict(list)
+        self._registry = {}                 # id(patch) -> patch, in first-insertion order (fill_with_point)
+        self._pending = []                  # [(records, colors)] accepted by the device, not yet objects
+        self._imgs = imgs
+        self._backend = None                # set by patch_expansion: callable -> DeviceBackend (for the filter)
         self.cell_size = cell_size
         for img in imgs:
             row, col = img.shape[0], img.shape[1]
             self.table.append(np.ones((math.ceil((col - 1) / cell_size), math.ceil((row - 1) / cell_size)), dtype=bool))
+
+    # -- the reference's attribute ---------------------------------------------------------------
+    @property
+    def Q_table(self):
+        self._materialise()
+        return self._Q
+
+    @Q_table.setter
+    def Q_table(self, value):
+        self._pending = []
+        self._Q = value
+
+    def _materialise(self):
+        for recs, colors in self._pending:
+            for p in _records_to_patches(recs, self._imgs, len(self.table), colors=colors):
+                self._registry[id(p)] = p
+                for hit in p.V:          # Q_table as MVS2.py:401-402 leaves it (fill_with_point once per hit)
+                    self._Q[(hit[0], math.floor(hit[1] / self.cell_size), math.floor(hit[2] / self.cell_size))].extend(
+                        [p] * len(p.V))
+        self._pending = []
+
+    def _add_records(self, recs, colors):
+        """Patches accepted by the device expansion (records in commit order)."""
+        if len(recs):
+            self._pending.append((recs, colors))
 
     def is_vacant(self, img_id, cell_i, cell_j):
         t = self.table[img_id]
@@ -178,8 +234,10 @@ class CellTable(object):
         if ci >= t.shape[0] or col < 0 or cj >= t.shape[1] or row < 0:
             raise IndexError("CellTable.fill_with_point: (%r, %r) is outside view %d" % (col, row, img_id))
         t[ci][cj] = False
+        self._materialise()
+        self._registry.setdefault(id(patch), patch)
         for idx, l_col, l_row in patch.V:          # sic: keyed by img_id for every entry (MVS2.py:106-107)
-            self.Q_table[(img_id, math.floor(l_col / self.cell_size), math.floor(l_row / self.cell_size))].append(patch)
+            self._Q[(img_id, math.floor(l_col / self.cell_size), math.floor(l_row / self.cell_size))].append(patch)
 
     def show_table_non_zeros(self):
         for i, t in enumerate(self.table):
@@ -194,12 +252,81 @@ class CellTable(object):
     def get_color(self, img, col, row):
         return img[int(row)][int(col)]
 
+    def _object_first_keys(self):
+        """Distinct MyPatch objects of the materialised part of Q with the first (view, ci, cj, position) at
+        which the reference's scan (MVS2.py:159-173) meets them."""
+        first = {}
+        for key in sorted(self._Q):
+            for pos, p in enumerate(self._Q[key]):
+                if id(p) not in first:
+                    first[id(p)] = (key[0], key[1], key[2], pos, p)
+        return list(first.values())
+
     def reconstruct_from_Q(self):
-        """MVS2.py:159-173: every distinct patch once, in table-scan order."""
-        import itertools
-        # first occurrence in (view, x-cell, y-cell) scan order; MyPatch hashes by identity
-        distinct = dict.fromkeys(itertools.chain.from_iterable(self.Q_table[key] for key in sorted(self.Q_table)))
-        return [p.c for p in distinct], [p.color for p in distinct]
+        """MVS2.py:159-173: every distinct patch once, in table-scan order (first key = lowest view of its
+        visible set; inside one list, insertion order).  Array path: no MyPatch objects are created for the
+        device-accepted patches."""
+        objs = self._object_first_keys()
+        if not self._pending:
+            return [o[4].c for o in objs], [o[4].color for o in objs]
+        cs = self.cell_size
+        V = len(self.table)
+        kv = [o[0] for o in objs]; ki = [o[1] for o in objs]; kj = [o[2] for o in objs]; ko = [o[3] for o in objs]
+        pts = [np.asarray(o[4].c, dtype=np.float64).reshape(3) for o in objs]
+        cols = [np.asarray(o[4].color).reshape(3) for o in objs]
+        P = [np.array(pts).reshape(-1, 3)]
+        Ccol = [np.array(cols).reshape(-1, 3)]
+        KV, KI, KJ, KO = [np.array(kv, np.int64)], [np.array(ki, np.int64)], [np.array(kj, np.int64)], [np.array(ko, np.int64)]
+        base = 1 << 40                                        # device patches come after every object of a list
+        for recs, colors in self._pending:
+            vis = unpack_vis(recs["vis"], V)
+            seen = vis.any(1)
+            KV.append(np.where(seen, vis.argmax(1), V).astype(np.int64)[seen])
+            KI.append(np.floor(recs["xy"][:, 0] / cs).astype(np.int64)[seen])
+            KJ.append(np.floor(recs["xy"][:, 1] / cs).astype(np.int64)[seen])
+            KO.append((base + np.arange(len(recs), dtype=np.int64))[seen])
+            base += len(recs)
+            P.append(np.ascontiguousarray(recs["c"])[seen])
+            Ccol.append(np.asarray(colors)[seen])
+        KV, KI, KJ, KO = (np.concatenate(x) for x in (KV, KI, KJ, KO))
+        order = np.lexsort((KO, KJ, KI, KV))
+        return list(np.concatenate(P)[order]), list(np.concatenate(Ccol)[order])
+
+    def _all_records(self):
+        """Every patch known to the table as records, in INSERTION order (objects first -- they were filled
+        before the device expansion ran -- then the device-accepted arrays), with a back-reference."""
+        V = len(self.table)
+        objs = list(self._registry.values())
+        parts = [_patches_to_records(objs, V)] if objs else []
+        parts += [r for r, _ in self._pending]
+        from .records import rec_dtype
+        return objs, (np.concatenate(parts) if parts else np.zeros(0, dtype=rec_dtype(V)))
+
+    def filter_out_outlier(self):
+        """MVS2.py:132-158 on the device (mvs_cells_filter): removes every outlier patch from all its Q
+        lists.  The reference leaves this pass disabled (MVS2.py:280-281); DensePointsWithMVS2 runs it when
+        MVS_FILTER_OUTLIERS=1."""
+        if self._backend is None:
+            raise MvsError("CellTable.filter_out_outlier needs the device context of this table: it is available after "
+                           "patch_expansion / DensePointsWithMVS2 ran on it (there is no CPU path)")
+        objs, recs = self._all_records()
+        be = self._backend(np.stack([np.asarray(t, dtype=np.uint8) for t in self.table]))
+        removed, n_removed, n_empty = be.filter(recs)
+        gone = set(id(o) for o, r in zip(objs, removed[:len(objs)]) if r)
+        if gone:
+            for key in list(self._Q):
+                self._Q[key] = [q for q in self._Q[key] if id(q) not in gone]
+            for i in gone:
+                self._registry.pop(i, None)
+        off = len(objs)
+        kept = []
+        for r, col in self._pending:
+            m = ~removed[off:off + len(r)]
+            off += len(r)
+            kept.append((r[m], np.asarray(col)[m]))
+        self._pending = [(r, c) for r, c in kept if len(r)]
+        print("filter_out_outlier: removed", n_removed, "patches;", n_empty, "non-vacant cells had no patch left")
+        return n_removed
 
 
 def is_patch_neighbor(patch, non_finished_patch, threshold=0.2):
@@ -218,16 +345,6 @@ def ray_plane_intersection(ray_origin, ray_direction, plane_center, plane_normal
 # ---------------------------------------------------------------------------------------
 # the two callers of the scorer
 # ---------------------------------------------------------------------------------------
-def _triangulate(P1, P2, x1, x2):
-    """utils.py:238-239 (cv2.triangulatePoints) for one correspondence -> homogeneous 4-vector."""
-    try:
-        import cv2
-        return cv2.triangulatePoints(P1, P2, np.array([x1]).transpose(), np.array([x2]).transpose()).transpose()[0]
-    except ImportError:
-        A = np.stack([x1[0] * P1[2] - P1[0], x1[1] * P1[2] - P1[1], x2[0] * P2[2] - P2[0], x2[1] * P2[2] - P2[1]])
-        return np.linalg.svd(A)[2][-1]
-
-
 def _patches_to_records(patches, V):
     vis = np.zeros((len(patches), V), dtype=bool)
     xy = np.zeros((len(patches), 2))
@@ -241,7 +358,23 @@ def _patches_to_records(patches, V):
                         vis)
 
 
-def _records_to_patches(recs, imgs, V):
+def _record_colors(recs, imgs):
+    """CellTable.get_color(imgs[ref], u, v) (MVS2.py:116-117,357) for device records: the pixel (px[0], px[1])
+    of the reference view, gathered view by view (no per-patch Python)."""
+    n = len(recs)
+    colors = np.zeros((n, 3), dtype=np.asarray(imgs[0]).dtype)
+    if n == 0:
+        return colors
+    px = recs["px"]
+    ref = np.asarray(recs["ref"])
+    has = px[:, 0] >= 0
+    for v in np.unique(ref[has]):
+        m = has & (ref == v)
+        colors[m] = np.asarray(imgs[int(v)])[px[m, 1], px[m, 0]]
+    return colors
+
+
+def _records_to_patches(recs, imgs, V, colors=None):
     """Device patch records -> MyPatch objects (the reference's carrier type).  Field extraction is
     done array-wise; only the object construction itself is per patch."""
     n = len(recs)
@@ -256,13 +389,9 @@ def _records_to_patches(recs, imgs, V):
     xy = recs["xy"].tolist()
     ref = recs["ref"].tolist()
     avg = recs["avg"].tolist()
-    px = recs["px"]
-    has_px = px[:, 0] >= 0
-    colors = np.zeros((n, 3), dtype=imgs[0].dtype)
-    if has_px.any():
-        stack_ref = np.asarray(recs["ref"])[has_px]
-        pr, pc = px[has_px, 1], px[has_px, 0]
-        colors[has_px] = [imgs[r][y][x] for r, y, x in zip(stack_ref.tolist(), pr.tolist(), pc.tolist())]
+    if colors is None:
+        colors = _record_colors(recs, imgs)
+    has_px = recs["px"][:, 0] >= 0
     out = []
     for k in range(n):
         x, y = xy[k]
@@ -273,52 +402,105 @@ def _records_to_patches(recs, imgs, V):
     return out
 
 
+def _dist_world():
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size(), dist
+    except ImportError:
+        pass
+    return 0, 1, None
+
+
 def patch_expansion(args, imgs, initial_patches, cells, camera_pos, visible_lower_bound):
-    """MVS2.py:308-404 restructured into synchronous device rounds (rounds.py).  Mutates
-    ``cells`` (vacancy grids + Q_table) like the reference; also returns the new patches."""
+    """MVS2.py:308-404 restructured into synchronous device rounds.  Mutates ``cells`` (vacancy grids +
+    Q_table) like the reference.  Default: the whole loop runs inside ONE C call (mvs_expand_run: one host
+    synchronisation per round; with several GPUs the accept decisions travel as a minimal wire over NVLink
+    stores, one device-side barrier per round).  MVS_ROUNDS=stepwise selects the per-phase driver
+    (rounds.RoundDriver: mvs_round_generate / score / commit, all-gather through torch.distributed)."""
     from .rounds import DeviceBackend, RoundDriver
     par_K, par_r, par_t = read_pars(args)
     V = len(imgs)
     ctx = _context(imgs, par_K, par_r, par_t)
+    if float(cells.cell_size) != int(cells.cell_size) or int(cells.cell_size) < 1:
+        raise MvsError("patch_expansion: the device cell table needs an integer cell_size >= 1 (got %r)" % (cells.cell_size,))
     table = np.stack([np.asarray(t, dtype=np.uint8) for t in cells.table])
-    be = DeviceBackend(ctx, cell_size=int(cells.cell_size), scale=float(args.scale), bound=int(visible_lower_bound),
-                       min_ncc=0.7, wid=5, table=table)
-    rank, world, group = 0, 1, None
-    try:
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized():
-            rank, world = dist.get_rank(), dist.get_world_size()
-    except ImportError:
-        pass
-    # multi-GPU exchange: fused into the compaction over NVLink P2P stores unless MVS_EXCHANGE=collective
-    drv = RoundDriver(be, rank=rank, world=world, group=group, timing=bool(os.environ.get("MVS_TIME_ROUNDS")),
-                      exchange=os.environ.get("MVS_EXCHANGE", "p2p"))
+
+    def backend(tab):
+        return DeviceBackend(ctx, cell_size=int(cells.cell_size), scale=float(args.scale), bound=int(visible_lower_bound),
+                             min_ncc=0.7, wid=5, table=tab)
+
+    be = backend(table)
+    cells._backend = backend
+    rank, world, dist = _dist_world()
     max_rounds = int(os.environ.get("MVS_MAX_ROUNDS", "100000"))
     max_iter = int(os.environ.get("MVS_MAX_ITERATIONS", "100000"))        # the reference's cap: iteration < 100000 (MVS2.py:321)
     max_patches = os.environ.get("MVS_MAX_PATCHES")
-    accepted = drv.run(be.to_device(_patches_to_records(initial_patches, V)), max_rounds=max_rounds,
-                       max_patches=int(max_patches) if max_patches else None, max_iterations=max_iter)
-    drv.finish_timing()
+    max_patches = int(max_patches) if max_patches else None
+    timing = bool(os.environ.get("MVS_TIME_ROUNDS"))
+    seeds = be.to_device(_patches_to_records(initial_patches, V))
+    mode = os.environ.get("MVS_ROUNDS", "fused")
+    if mode == "fused" and world > 1:
+        # the fused exchange needs NCCL-style symmetric memory with peer access on ONE box: agree on it
+        # collectively, otherwise every rank falls back to the stepwise driver with a collective all-gather
+        import torch
+        ok = 1
+        try:
+            if dist.get_backend() != "nccl":
+                raise RuntimeError("backend is not nccl")
+            be.exchange_setup(int(os.environ.get("MVS_ROUND_CAPACITY", str(1 << 21))), world, dist.group.WORLD)
+        except Exception as e:                                # noqa: any failure -> collective fallback
+            ok = 0
+            why = repr(e)
+        flag = torch.tensor([ok], dtype=torch.int32, device=be.device if dist.get_backend() == "nccl" else "cpu")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            if rank == 0:
+                print("patch_expansion: fused P2P exchange unavailable (%s); using the collective all-gather" % (why if not ok else "on a peer"))
+            mode = "stepwise"
+    if mode == "fused":
+        stats, n_new = be.expand_run(seeds, max_rounds=max_rounds, max_iterations=max_iter, max_patches=max_patches,
+                                     rank=rank, world=world, timing=timing)
+        recs = be.expand_result(0, n_new)
+    else:
+        exchange = os.environ.get("MVS_EXCHANGE", "collective")
+        drv = RoundDriver(be, rank=rank, world=world, group=None, timing=timing, exchange=exchange)
+        accepted = drv.run(seeds, max_rounds=max_rounds, max_patches=max_patches, max_iterations=max_iter)
+        drv.finish_timing()
+        stats = drv.stats
+        from .records import rec_dtype
+        recs = np.concatenate([be.to_host(r) for r in accepted]) if accepted else np.zeros(0, dtype=rec_dtype(V))
     new_tab = be.table()
     for v in range(V):
         cells.table[v][...] = new_tab[v]
-    new_patches = []
-    for rnd in accepted:
-        new_patches.extend(_records_to_patches(be.to_host(rnd), imgs, V))
-    for p in new_patches:                                  # Q_table as MVS2.py:401-402 leaves it
-        for hit in p.V:
-            cells.Q_table[(hit[0], math.floor(hit[1] / cells.cell_size), math.floor(hit[2] / cells.cell_size))].extend(
-                [p] * len(p.V))
+    cells._add_records(recs, _record_colors(recs, imgs))
     if getattr(args, "debug", False):
-        for i, st in enumerate(drv.stats):
+        for i, st in enumerate(stats):
             print("round", i + 1, st)
-    print("expansion rounds:", len(drv.stats), "new patches:", len(new_patches))
-    patch_expansion.last_stats = drv.stats
-    return new_patches
+    print("expansion rounds:", len(stats), "new patches:", len(recs))
+    patch_expansion.last_stats = stats
+    patch_expansion.last_records = recs
+
+
+def _flatten_tracks(legal_sets, n_cameras):
+    """SfM tracks (GlobalSet.getInfo(): legal_set.point2d_list = [(view, x, y), ...]) as a flat observation
+    array + offsets, the input layout of mvs_seed_stage."""
+    obs, offsets = [], [0]
+    for legal_set in legal_sets:
+        for cam, px, py in legal_set.point2d_list:
+            if cam >= n_cameras:
+                raise IndexError("track observation refers to view %d of %d" % (cam, n_cameras))
+            obs.append((float(cam), float(px), float(py)))
+        offsets.append(len(obs))
+    return np.array(obs, dtype=np.float64).reshape(-1, 3), np.array(offsets, dtype=np.int64)
 
 
 def DensePointsWithMVS2(imgs, global_set, args):
-    """MVS2.py:176-295: seed patches from the SfM tracks, expansion, point cloud export."""
+    """MVS2.py:176-295: seed patches from the SfM tracks, expansion, point cloud export.  The seed stage
+    (triangulation of every track candidate, scoring at MIN_NCC 0.4, nearest-first pick) runs on the device
+    in one call (mvs_seed_stage); MVS_FILTER_OUTLIERS=1 also runs CellTable.filter_out_outlier, which the
+    reference ships disabled (MVS2.py:280-281)."""
+    from .rounds import DeviceBackend
     t0 = time.time()
     par_K, par_r, par_t = read_pars(args)
     n_observations, n_world_points, legal_sets = global_set.getInfo()
@@ -326,56 +508,48 @@ def DensePointsWithMVS2(imgs, global_set, args):
     camera_pos = [-(par_r[i].transpose() @ par_t[i].reshape(3, -1)).reshape(-1) for i in range(n_cameras)]
     cells = CellTable(imgs, cell_size=args.cell_size)
     visible_lower_bound = 3 if n_cameras > 2 else 2
+    _, _, dist_mod = _dist_world()
+    rank = dist_mod.get_rank() if dist_mod is not None else 0
 
-    # every (track, other observation) candidate of MVS2.py:223-250, scored in ONE batch at MIN_NCC 0.4
-    cand, owner = [], []
-    for ti, legal_set in enumerate(legal_sets):
-        ref, base, O = None, None, None
-        for ct, (cam, px, py) in enumerate(legal_set.point2d_list):
-            if cam >= n_cameras:
-                raise IndexError("track observation refers to view %d of %d" % (cam, n_cameras))
-            pt = [float(px), float(py)]
-            if ct == 0:
-                ref, base, O = cam, pt, camera_pos[cam]
-                P1 = par_K[ref] @ np.concatenate((par_r[ref], par_t[ref]), axis=1)
-                continue
-            P2 = par_K[cam] @ np.concatenate((par_r[cam], par_t[cam]), axis=1)
-            un = _triangulate(P1, P2, base, pt)
-            c = 0 * un[:-1] if un[-1] == 0 else un[:-1] / un[-1]
-            dist = math.sqrt(((c - O) ** 2).sum())
-            n = (O - c) / dist
-            color = cells.get_color(imgs[cam], px, py)
-            cand.append(MyPatch(c, n, ref, None, color, dist))
-            owner.append(ti)
+    obs, offsets = _flatten_tracks(legal_sets, n_cameras)
     initial_patches = []
-    if cand:
+    if len(obs):
         ctx = _context(imgs, par_K, par_r, par_t)
-        out = ctx.score_host(np.array([p.c for p in cand]), np.array([p.R for p in cand], dtype=np.int32), min_ncc=0.4, wid=5)
-        vis = unpack_vis(out["vis_mask"], ctx.V)
-        for k, p in enumerate(cand):
-            x, y = float(out["xy"][k, 0]), float(out["xy"][k, 1])
-            p.V = [[int(v), x, y] for v in np.nonzero(vis[k])[0]]
-            p.avg_ncc_score = float(out["avg"][k])
-        by_track = defaultdict(list)
-        for p, ti in zip(cand, owner):
-            by_track[ti].append(p)
-        for ti in sorted(by_track):                          # nearest-first, first with enough views wins (MVS2.py:253-260)
-            heap = MyPatchHeapSort(by_track[ti])
-            while heap.size() != 0:
-                p = heap.pop()
-                if p.visible_ct() >= visible_lower_bound:
-                    initial_patches.append(p)
-                    for hit in p.V:
-                        cells.fill_with_point(hit[0], hit[1], hit[2], p)
-                    break
+        cs = int(args.cell_size) if float(args.cell_size) == int(args.cell_size) and args.cell_size >= 1 else 1
+        be = DeviceBackend(ctx, cell_size=cs, scale=float(args.scale), bound=visible_lower_bound, min_ncc=0.7, wid=5)
+        P = np.stack([par_K[v] @ np.concatenate((par_r[v], par_t[v].reshape(3, 1)), axis=1) for v in range(n_cameras)])   # utils.py:234-236
+        recs = be.seed_stage(obs, offsets, P, min_ncc=0.4)
+        # candidate number -> observation it was triangulated with (every observation but the first of its track)
+        first = np.zeros(len(obs), dtype=bool)
+        lens = np.diff(offsets)
+        first[offsets[:-1][lens > 0]] = True
+        cand_obs = np.nonzero(~first)[0]
+        vis = unpack_vis(recs["vis"], n_cameras)
+        for k in range(len(recs)):
+            o = obs[cand_obs[int(recs["index"][k])]]
+            c = np.array(recs["c"][k])
+            ref = int(recs["ref"][k])
+            x, y = float(recs["xy"][k, 0]), float(recs["xy"][k, 1])
+            O = camera_pos[ref]
+            p = MyPatch(c, np.array(recs["n"][k]), ref, [[int(v), x, y] for v in np.nonzero(vis[k])[0]],
+                        cells.get_color(imgs[int(o[0])], o[1], o[2]), math.sqrt(((c - O) ** 2).sum()))
+            p.avg_ncc_score = float(recs["avg"][k])
+            initial_patches.append(p)
+            for hit in p.V:
+                cells.fill_with_point(hit[0], hit[1], hit[2], p)
     print("len of initial patches", len(initial_patches))
-    export2ply(np.array([p.c for p in initial_patches]).reshape(-1, 3),
-               np.array([p.color for p in initial_patches]).reshape(-1, 3), path="initial_patches")
+    if rank == 0:
+        export2ply(np.array([p.c for p in initial_patches]).reshape(-1, 3),
+                   np.array([p.color for p in initial_patches]).reshape(-1, 3), path="initial_patches")
 
     patch_expansion(args, imgs, initial_patches, cells, camera_pos, visible_lower_bound)
 
+    if os.environ.get("MVS_FILTER_OUTLIERS"):
+        print("filter outliers")
+        cells.filter_out_outlier()
     print("reconstruct point cloud")
     points_3d, colors = cells.reconstruct_from_Q()
     print("Optimization took {0:.0f} seconds".format(time.time() - t0))
     print("points len:", len(points_3d))
-    export2ply(np.array(points_3d).reshape(-1, 3), np.array(colors).reshape(-1, 3), path="all_patches")
+    if rank == 0:
+        export2ply(np.array(points_3d).reshape(-1, 3), np.array(colors).reshape(-1, 3), path="all_patches")

@@ -42,10 +42,35 @@ SYMBOLS = {
                                       C.c_int, C.c_int, C.c_int64, _P]),
     "mvs_round_commit": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P]),
     "mvs_round_candidates": (C.c_int, [_P, _P, _P, _P, _P, _P]),
+    "mvs_exchange_bytes": (C.c_int64, [_P, C.c_int, C.c_int64]),
+    "mvs_publish_accepted": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, C.c_int, _P, C.c_int, C.c_int, C.c_int64, C.c_int, _P]),
+    "mvs_p2p_barrier": (C.c_int, [_P, _P, C.c_int, C.c_int, _P]),
+    "mvs_p2p_barrier_failed": (C.c_int, [_P, _P]),
+    "mvs_expand_run": (C.c_int, [_P, _P, C.c_int64, _P, _P, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int64), _P]),
+    "mvs_expand_result": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int, _P]),
+    "mvs_cells_filter": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P]),
+    "mvs_triangulate": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P, _P]),
+    "mvs_seed_stage": (C.c_int, [_P, C.c_int64, _P, _P, _P, C.c_double, C.c_int, C.c_int, _P, C.c_void_p, _P]),
     "mvs_ncc_pairs": (C.c_int, [C.c_int, C.c_int64, C.c_int, _P, _P, _P, C.c_int, _P]),
     "mvs_compact_accepted": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, _P, C.c_int64,
                                        _P, _P]),
 }
+
+
+
+class ExpandParams(C.Structure):
+    """mvs_expand_params (include/mvs_ncc.h)."""
+    _fields_ = [("min_ncc", C.c_double), ("scale", C.c_double), ("wid", C.c_int32), ("bound", C.c_int32),
+                ("max_rounds", C.c_int64), ("max_iterations", C.c_int64), ("max_patches", C.c_int64),
+                ("rank", C.c_int32), ("world", C.c_int32), ("peer_inbox", C.c_void_p), ("peer_flags", C.c_void_p),
+                ("capacity", C.c_int64), ("timing", C.c_int32), ("reserved", C.c_int32)]
+
+
+class RoundStat(C.Structure):
+    """mvs_round_stat (include/mvs_ncc.h)."""
+    _fields_ = [("frontier", C.c_int64), ("candidates", C.c_int64), ("passed", C.c_int64), ("accepted", C.c_int64),
+                ("ms", C.c_float), ("reserved", C.c_int32)]
+
 
 _lib = None
 

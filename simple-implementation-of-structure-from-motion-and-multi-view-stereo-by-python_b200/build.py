@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(HERE, "libmvsncc.so")
-SOURCES = ["mvs_api.cu", "ncc_refexact.cu", "ncc_pmvs.cu", "bin.cu", "compact.cu", "scan.cu", "expand.cu", "ncc_pairs.cu"]
+SOURCES = ["mvs_api.cu", "ncc_refexact.cu", "ncc_pmvs.cu", "bin.cu", "compact.cu", "scan.cu", "expand.cu", "ncc_pairs.cu", "exchange.cu", "seeds.cu", "filter.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC"]
 OBJ_DIR = os.path.join(HERE, "build")

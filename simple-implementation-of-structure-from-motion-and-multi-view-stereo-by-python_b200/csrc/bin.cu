@@ -121,7 +121,7 @@ int mvs_bin_hypotheses(mvs_ctx* ctx, int64_t N, const double* c, const int32_t* 
     if (sort) {
         int64_t* d_total = ctx->d_bin_scan + (n_tiles + 1 + 1023) / 1024;
         if ((rc = mvs_exclusive_scan_i32(ctx->d_bin_hist, n_tiles + 1, ctx->d_bin_scan, d_total, s)) != MVS_OK) return rc;
-        ctx->launches += 3;
+        ctx->launches += mvs_scan_launches(n_tiles + 1);
         bin_scatter<<<(int)blocks, 256, 0, s>>>(N, ctx->d_bin_hist, ctx->d_bin_key, ctx->d_bin_rank, ctx->d_bin_anchor,
                                                 (uint2*)ctx->d_bin_entry);
         ctx->launches++;

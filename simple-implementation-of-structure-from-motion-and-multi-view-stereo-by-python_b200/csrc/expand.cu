@@ -53,8 +53,18 @@ __global__ void __launch_bounds__(128)
                  const uint8_t* __restrict__ cells, unsigned long long* __restrict__ claim, unsigned epoch,
                  int32_t* __restrict__ counts /*[F]*/, const CamGeom* __restrict__ geom, int64_t* __restrict__ cand_slot,
                  int64_t* __restrict__ cand_parent, double* __restrict__ cand_c, double* __restrict__ cand_n,
-                 int32_t* __restrict__ cand_ref, int32_t* __restrict__ cand_px) {
+                 int32_t* __restrict__ cand_ref, int32_t* __restrict__ cand_px, const int64_t* __restrict__ d_F = nullptr,
+                 int64_t F_clamp = 0) {
     const int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (d_F) {
+        // frontier size still on the device (the commit that produced it has not been read back): the grid
+        // covers an upper bound `F`, threads past the real size only zero their count
+        const int64_t Fd = *d_F < F_clamp ? *d_F : F_clamp;
+        if (f >= Fd) {
+            if (PASS == 1 && f < F) counts[f] = 0;
+            return;
+        }
+    }
     if (f >= F) return;
     const mvs_patch_record* p = rec_at(frontier, f, rec_bytes);
     const uint64_t* vis = rec_vis(p);
@@ -294,7 +304,7 @@ extern "C" int mvs_round_generate(mvs_ctx* ctx, const void* frontier, int64_t F,
     ctx->launches += 2;
     MVS_CUDA_CHECK(cudaGetLastError());
     if ((rc = mvs_exclusive_scan_i32(ctx->d_counts, F, ctx->d_scan, d_total, s)) != MVS_OK) return rc;
-    ctx->launches += 3;
+    ctx->launches += mvs_scan_launches(F);
     int64_t M = 0;
     MVS_CUDA_CHECK(cudaMemcpyAsync(&M, d_total, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
     MVS_CUDA_CHECK(cudaStreamSynchronize(s));
@@ -398,7 +408,7 @@ extern "C" int mvs_round_commit(mvs_ctx* ctx, const void* records, int64_t n, vo
     if ((rc = mvs_exclusive_scan_i32(ctx->d_counts, n, ctx->d_scan, n_next, s)) != MVS_OK) return rc;
     commit_apply<<<blocks, 256, 0, s>>>((const uint8_t*)records, n, rb, ctx->d_counts, n_next, (uint8_t*)next_frontier, ctx->V,
                                        ctx->cell_size, ctx->wc, ctx->hc, ctx->d_cells);
-    ctx->launches += 5;
+    ctx->launches += 2 + mvs_scan_launches(n);
     MVS_CUDA_CHECK(cudaGetLastError());
     return MVS_OK;
 }
@@ -414,5 +424,230 @@ extern "C" int mvs_round_candidates(mvs_ctx* ctx, int64_t* slot, int64_t* parent
     if (c) MVS_CUDA_CHECK(cudaMemcpy(c, ctx->cand_c, sizeof(double) * 3 * M, cudaMemcpyDeviceToHost));
     if (nrm) MVS_CUDA_CHECK(cudaMemcpy(nrm, ctx->cand_n, sizeof(double) * 3 * M, cudaMemcpyDeviceToHost));
     if (ref) MVS_CUDA_CHECK(cudaMemcpy(ref, ctx->cand_ref, sizeof(int32_t) * M, cudaMemcpyDeviceToHost));
+    return MVS_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------
+// The whole expansion loop on the host side of the C ABI (replaces the while-loop of MVS2.py:321-404 for
+// ALL rounds in one call): no Python between rounds and ONE host synchronisation per round.
+//   round k:  expand_slots<2> (candidates)  ->  score this GPU's shard + gate  ->  publish the minimal wire
+//             into every GPU's inbox  ->  [device barrier]  ->  commit from the wire (next frontier appended
+//             to the context's output buffer, cells filled)  ->  expand_slots<0,1> + scan of round k+1 run
+//             SPECULATIVELY on the device-side frontier size  ->  one read-back of {accepted, next M}.
+// Every GPU executes the same sequence on the same candidate list, so all ranks stay in lockstep without
+// any host communication.
+// ---------------------------------------------------------------------------------------
+int mvs_launch_publish(mvs_ctx* ctx, int64_t N, const uint64_t* vis, const double* avg, const int32_t* count,
+                       const uint8_t* gate, int bound, void* const* peer_inbox, int rank, int world, int64_t capacity,
+                       int parity, cudaStream_t s);
+int mvs_launch_commit_wire(mvs_ctx* ctx, const void* inbox_local, int world, int64_t capacity, int parity, int64_t M,
+                           void* next_frontier, int64_t* d_n_next, cudaStream_t s);
+
+// grow a device buffer, KEEPING its first `keep` bytes
+static int ensure_keep(void** p, size_t* cap, size_t bytes, size_t keep, cudaStream_t s, const char* what) {
+    if (bytes <= *cap && *p) return MVS_OK;
+    void* q = nullptr;
+    const size_t want = bytes * 2 + 4096;
+    if (cudaMalloc(&q, want) != cudaSuccess) {
+        cudaGetLastError();
+        mvs_set_error("device allocation of %zu bytes for %s failed", want, what);
+        return MVS_ERR_NOMEM;
+    }
+    if (*p && keep) {
+        MVS_CUDA_CHECK(cudaMemcpyAsync(q, *p, keep, cudaMemcpyDeviceToDevice, s));
+        MVS_CUDA_CHECK(cudaStreamSynchronize(s));
+    }
+    if (*p) cudaFree(*p);
+    *p = q;
+    *cap = want;
+    return MVS_OK;
+}
+
+// claim + count passes of candidate generation for a frontier whose size is host-known (d_F == nullptr) or
+// still on the device (grid over the upper bound F_upper); leaves the candidate count in *d_total
+static int generate_count(mvs_ctx* ctx, const void* frontier, int64_t F_upper, const int64_t* d_F, int64_t F_clamp,
+                          int64_t** d_total_out, cudaStream_t s) {
+    int rc;
+    if ((rc = mvs_ensure((void**)&ctx->d_counts, &ctx->counts_bytes, sizeof(int32_t) * F_upper, "slot counts")) != MVS_OK) return rc;
+    if ((rc = mvs_ensure((void**)&ctx->d_scan, &ctx->scan_bytes, sizeof(int64_t) * ((F_upper + 1023) / 1024 + 2), "scan")) != MVS_OK) return rc;
+    ctx->epoch++;
+    const int rb = rec_bytes_of(ctx);
+    const unsigned blocks = (unsigned)((F_upper + 127) / 128);
+    int64_t* d_total = ctx->d_scan + (F_upper + 1023) / 1024;
+    expand_slots<0><<<blocks, 128, 0, s>>>((const uint8_t*)frontier, F_upper, rb, ctx->V, ctx->cell_size, ctx->wc, ctx->hc,
+                                          ctx->d_cells, ctx->d_claim, ctx->epoch, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                          nullptr, nullptr, nullptr, d_F, F_clamp);
+    expand_slots<1><<<blocks, 128, 0, s>>>((const uint8_t*)frontier, F_upper, rb, ctx->V, ctx->cell_size, ctx->wc, ctx->hc,
+                                          ctx->d_cells, ctx->d_claim, ctx->epoch, ctx->d_counts, nullptr, nullptr, nullptr,
+                                          nullptr, nullptr, nullptr, nullptr, d_F, F_clamp);
+    ctx->launches += 2;
+    MVS_CUDA_CHECK(cudaGetLastError());
+    if ((rc = mvs_exclusive_scan_i32(ctx->d_counts, F_upper, ctx->d_scan, d_total, s)) != MVS_OK) return rc;
+    ctx->launches += mvs_scan_launches(F_upper);
+    *d_total_out = d_total;
+    return MVS_OK;
+}
+
+extern "C" int mvs_expand_run(mvs_ctx* ctx, const void* seeds, int64_t n_seeds, const mvs_expand_params* prm,
+                              mvs_round_stat* stats, int max_stats, int* n_rounds, int64_t* n_patches, void* stream) {
+    if (!ctx || !ctx->d_cells) { mvs_set_error("mvs_expand_run: cell table not initialised (mvs_cells_init)"); return MVS_ERR_STATE; }
+    if (!prm || n_seeds < 0 || (n_seeds > 0 && !seeds) || !n_rounds || !n_patches || prm->wid < 1 || prm->wid > 7 ||
+        prm->world < 1 || prm->world > MVS_MAX_PEERS || prm->rank < 0 || prm->rank >= prm->world ||
+        (prm->world > 1 && (!prm->peer_inbox || !prm->peer_flags || prm->capacity < 1))) {
+        mvs_set_error("mvs_expand_run: bad argument (need params, 1 <= wid <= 7, 0 <= rank < world <= %d and, for world > 1, "
+                      "the inbox / flag tables and a capacity)", MVS_MAX_PEERS);
+        return MVS_ERR_ARG;
+    }
+    MVS_CUDA_CHECK(cudaSetDevice(ctx->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const int world = prm->world, rank = prm->rank;
+    const int rb = rec_bytes_of(ctx);
+    const size_t mw = (size_t)((ctx->V + 63) / 64);
+    const int64_t max_rounds = prm->max_rounds < 0 ? (1ll << 40) : prm->max_rounds;
+    const int64_t max_iter = prm->max_iterations < 0 ? (1ll << 60) : prm->max_iterations;
+    const int64_t max_patches = prm->max_patches < 0 ? (1ll << 60) : prm->max_patches;
+    *n_rounds = 0;
+    *n_patches = 0;
+    ctx->n_out = 0;
+    int rc;
+    if (!ctx->h_pinned) MVS_CUDA_CHECK(cudaMallocHost(&ctx->h_pinned, 256));
+    int64_t* h_back = (int64_t*)ctx->h_pinned;                 // {n_next, next M} + per-rank kept counts
+    if (prm->timing && !ctx->ev_round[0]) {
+        MVS_CUDA_CHECK(cudaEventCreate(&ctx->ev_round[0]));
+        MVS_CUDA_CHECK(cudaEventCreate(&ctx->ev_round[1]));
+    }
+    int64_t* d_n_next = nullptr;
+    if ((rc = mvs_ensure((void**)&ctx->d_round_n, &ctx->round_n_bytes, 64, "round counters")) != MVS_OK) return rc;
+    d_n_next = ctx->d_round_n;
+
+    int64_t F = n_seeds, expanded = 0, T = 0;                  // T = accepted records so far (offset of the next frontier)
+    const uint8_t* frontier = (const uint8_t*)seeds;
+    bool frontier_in_out = false;
+    int64_t frontier_off = 0;
+    if (max_iter < F) F = max_iter;
+    if (F == 0 || max_rounds == 0) return MVS_OK;
+    if (F * (int64_t)ctx->V * 4 >= (1ll << 40)) { mvs_set_error("frontier too large for the slot encoding"); return MVS_ERR_ARG; }
+    int64_t* d_total = nullptr;
+    if ((rc = generate_count(ctx, frontier, F, nullptr, 0, &d_total, s)) != MVS_OK) return rc;
+    int64_t M = 0;
+    MVS_CUDA_CHECK(cudaMemcpyAsync(&h_back[1], d_total, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    MVS_CUDA_CHECK(cudaStreamSynchronize(s));
+    M = h_back[1];
+
+    for (int64_t k = 0; k < max_rounds; ++k) {
+        if (F == 0) break;
+        if (M >= (1ll << 31)) { mvs_set_error("more than 2^31 candidates in one round"); return MVS_ERR_ARG; }
+        expanded += F;
+        if (prm->timing) MVS_CUDA_CHECK(cudaEventRecord(ctx->ev_round[0], s));
+        int64_t n_next = 0, M_next = 0, passed = 0;
+        int64_t F_next_upper = 0;
+        if (M > 0) {
+            const int64_t shard_cap = world > 1 ? prm->capacity : M;
+            if (world > 1 && (M + world - 1) / world > shard_cap) {
+                mvs_set_error("mvs_expand_run: round %lld has %lld candidates, more than the inbox capacity of %lld per GPU x %d GPUs",
+                              (long long)k, (long long)M, (long long)shard_cap, world);
+                return MVS_ERR_STATE;
+            }
+            if ((rc = ensure_candidates(ctx, M)) != MVS_OK) return rc;
+            if ((rc = ensure_keep((void**)&ctx->d_out, &ctx->out_bytes, (size_t)(T + M) * rb, (size_t)T * rb, s, "accepted patches")) != MVS_OK)
+                return rc;
+            if (frontier_in_out) frontier = ctx->d_out + frontier_off * rb;   // the buffer may have moved
+            // ---- candidates of this round
+            expand_slots<2><<<(unsigned)((F + 127) / 128), 128, 0, s>>>(frontier, F, rb, ctx->V, ctx->cell_size, ctx->wc, ctx->hc,
+                                                                        ctx->d_cells, ctx->d_claim, ctx->epoch, ctx->d_counts,
+                                                                        ctx->d_geom, ctx->cand_slot, ctx->cand_parent, ctx->cand_c,
+                                                                        ctx->cand_n, ctx->cand_ref, ctx->cand_px);
+            ctx->launches++;
+            MVS_CUDA_CHECK(cudaGetLastError());
+            ctx->n_cand = M;
+            // ---- this GPU's shard: score, gate, publish
+            const int64_t begin = (M * rank) / world, end = (M * (rank + 1)) / world;
+            if ((rc = round_score_shard(ctx, frontier, begin, end, prm->min_ncc, prm->wid, prm->scale, s)) != MVS_OK) return rc;
+            void* local_tab[1];
+            void* const* inbox_tab = prm->peer_inbox;
+            const void* inbox_local;
+            if (world == 1) {
+                const size_t need = (size_t)mvs_exchange_bytes(ctx, 1, shard_cap);
+                if ((rc = mvs_ensure((void**)&ctx->d_inbox, &ctx->inbox_bytes, need, "local inbox")) != MVS_OK) return rc;
+                local_tab[0] = ctx->d_inbox;
+                inbox_tab = local_tab;
+                inbox_local = ctx->d_inbox;
+            } else {
+                inbox_local = prm->peer_inbox[rank];
+            }
+            const int parity = (int)(k & 1);
+            if ((rc = mvs_launch_publish(ctx, end - begin, ctx->cand_vis + mw * begin, ctx->cand_avg + begin, ctx->cand_count + begin,
+                                         ctx->cand_gate + begin, prm->bound, inbox_tab, rank, world, shard_cap, parity, s)) != MVS_OK)
+                return rc;
+            if (world > 1 && (rc = mvs_p2p_barrier(ctx, prm->peer_flags, rank, world, s)) != MVS_OK) return rc;
+            // ---- commit (identical on every GPU): next frontier appended to the output buffer
+            uint8_t* next = ctx->d_out + T * rb;
+            if ((rc = mvs_launch_commit_wire(ctx, inbox_local, world, shard_cap, parity, M, next, d_n_next, s)) != MVS_OK) return rc;
+            // kept-per-rank headers of this round (statistics)
+            MVS_CUDA_CHECK(cudaMemcpy2DAsync(&h_back[2], sizeof(int64_t),
+                                             (const uint8_t*)inbox_local + (size_t)parity * world * (mvs_exchange_bytes(ctx, world, shard_cap) / (2 * world)),
+                                             (size_t)(mvs_exchange_bytes(ctx, world, shard_cap) / (2 * world)), sizeof(int64_t), world,
+                                             cudaMemcpyDeviceToHost, s));
+            // ---- speculative claim + count passes of the NEXT round on the device-side frontier size
+            const int64_t remaining = max_iter - expanded;
+            if (k + 1 < max_rounds && remaining > 0) {
+                F_next_upper = M;                              // accepted <= candidates
+                if ((rc = generate_count(ctx, next, F_next_upper, d_n_next, remaining, &d_total, s)) != MVS_OK) return rc;
+                MVS_CUDA_CHECK(cudaMemcpyAsync(&h_back[1], d_total, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+            } else {
+                h_back[1] = 0;
+            }
+            MVS_CUDA_CHECK(cudaMemcpyAsync(&h_back[0], d_n_next, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+            if (prm->timing) MVS_CUDA_CHECK(cudaEventRecord(ctx->ev_round[1], s));
+            MVS_CUDA_CHECK(cudaStreamSynchronize(s));
+            n_next = h_back[0];
+            M_next = h_back[1];
+            for (int r = 0; r < world; ++r) passed += h_back[2 + r];
+            if (world > 1 && mvs_p2p_barrier_failed(ctx, s)) {
+                mvs_set_error("mvs_expand_run: a peer GPU did not reach the round barrier (round %lld)", (long long)k);
+                return MVS_ERR_STATE;
+            }
+        } else if (prm->timing) {
+            MVS_CUDA_CHECK(cudaEventRecord(ctx->ev_round[1], s));
+            MVS_CUDA_CHECK(cudaStreamSynchronize(s));
+        }
+        if (stats && *n_rounds < max_stats) {
+            mvs_round_stat& st = stats[*n_rounds];
+            st.frontier = F;
+            st.candidates = M;
+            st.passed = passed;
+            st.accepted = n_next;
+            st.ms = 0.f;
+            if (prm->timing) cudaEventElapsedTime(&st.ms, ctx->ev_round[0], ctx->ev_round[1]);
+        }
+        ++*n_rounds;
+        frontier_in_out = true;
+        frontier_off = T;
+        frontier = ctx->d_out + T * rb;
+        T += n_next;
+        ctx->n_out = T;
+        const int64_t remaining = max_iter - expanded;
+        F = n_next < remaining ? n_next : remaining;
+        M = M_next;
+        if (T >= max_patches) break;
+    }
+    *n_patches = T;
+    return MVS_OK;
+}
+
+extern "C" int mvs_expand_result(mvs_ctx* ctx, void* records, int64_t offset, int64_t n, int on_device, void* stream) {
+    if (!ctx) { mvs_set_error("mvs_expand_result: null context"); return MVS_ERR_ARG; }
+    if (offset < 0 || n < 0 || offset + n > ctx->n_out || (n > 0 && !records)) {
+        mvs_set_error("mvs_expand_result: records [%lld, %lld) requested, %lld available", (long long)offset, (long long)(offset + n),
+                      (long long)ctx->n_out);
+        return MVS_ERR_ARG;
+    }
+    if (n == 0) return MVS_OK;
+    MVS_CUDA_CHECK(cudaSetDevice(ctx->device));
+    const size_t rb = (size_t)rec_bytes_of(ctx);
+    MVS_CUDA_CHECK(cudaMemcpyAsync(records, ctx->d_out + offset * rb, n * rb, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                                   (cudaStream_t)stream));
+    if (!on_device) MVS_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
     return MVS_OK;
 }

@@ -237,6 +237,12 @@ extern "C" int mvs_destroy(mvs_ctx* ctx) {
                     ctx->cand_gate};
     for (void* b : bufs)
         if (b) cudaFree(b);
+    void* more2[] = {ctx->d_out, ctx->d_inbox, ctx->d_round_n, ctx->d_barrier_state};
+    for (void* b : more2)
+        if (b) cudaFree(b);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    for (int i = 0; i < 2; ++i)
+        if (ctx->ev_round[i]) cudaEventDestroy(ctx->ev_round[i]);
     for (int i = 0; i < 2 * MVS_PROF_RING; ++i)
         if (ctx->prof_ev[i]) cudaEventDestroy(ctx->prof_ev[i]);
     if (ctx->in_stream) cudaStreamDestroy(ctx->in_stream);

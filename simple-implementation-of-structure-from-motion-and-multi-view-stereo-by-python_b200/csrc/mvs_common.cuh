@@ -116,7 +116,20 @@ struct mvs_ctx {
     double* cand_xy;
     uint8_t* cand_gate;
     size_t cand_cap[11];
+    // fused round pipeline (mvs_expand_run) and exchange (exchange.cu)
+    uint8_t* d_out;                   // accepted patch records of all rounds, in commit order
+    size_t out_bytes;
+    int64_t n_out;
+    uint8_t* d_inbox;                 // world == 1: the local "inbox" of the minimal wire
+    size_t inbox_bytes;
+    int64_t* d_round_n;
+    size_t round_n_bytes;
+    void* d_barrier_state;            // {u64 epoch, int error}
+    void* h_pinned;                   // small pinned read-back area
+    cudaEvent_t ev_round[2];
 };
+
+int mvs_p2p_barrier_failed(mvs_ctx* ctx, void* stream);
 
 void mvs_set_error(const char* fmt, ...);
 

@@ -1037,7 +1037,16 @@ static int launch_gather(mvs_ctx* ctx, const ScoreArgs& A, int64_t N, const uint
     if (Q <= 8) return launch_gather_gs<WID, 8, 0>(ctx, A, N, anchors, entries, s);
     // 33..48 views: eight lanes per block, six views per lane (needs a window that fits the image for its idle groups)
     if (Q > 8 && Q <= 12 && !k1_legacy() && ctx->H >= 2 * WID + 2 && ctx->W >= 2 * WID + 3) {
-        if (WID == 5 && Q == 12) return launch_gather6<5, 192>(ctx, A, N, anchors, entries, s);
+        if (WID == 5 && Q == 12) {
+            static int mb = -1;                            // MVS_K6_MINB: resident CTAs per SM (tuning knob)
+            if (mb < 0) {
+                const char* e = getenv("MVS_K6_MINB");
+                mb = e ? atoi(e) : 0;
+            }
+            if (mb == 2) return launch_gather6<5, 192, 2>(ctx, A, N, anchors, entries, s);
+            if (mb == 4) return launch_gather6<5, 192, 4>(ctx, A, N, anchors, entries, s);
+            return launch_gather6<5, 192>(ctx, A, N, anchors, entries, s);
+        }
         return launch_gather6<WID, 0>(ctx, A, N, anchors, entries, s);
     }
     if (Q <= 16) {

@@ -82,9 +82,33 @@ __global__ void __launch_bounds__(1024) scan_add_base(int32_t* __restrict__ a, i
     if (i < n) a[i] += (int32_t)tile_tot[blockIdx.x];
 }
 
+// One CTA, one launch: thread t scans the run [t*per, (t+1)*per) serially, the 1024 run totals are scanned
+// block-wide.  For the small arrays of a real expansion round (frontier, candidates, histogram bins),
+// where three dependent launches cost more than the scan itself.
+#define MVS_SCAN_SMALL_MAX (1024 * 160)
+__global__ void __launch_bounds__(1024) scan_small(int32_t* __restrict__ a, int n, int per, int64_t* __restrict__ total) {
+    __shared__ int wsum[32];
+    const int lo = threadIdx.x * per, hi = min(lo + per, n);
+    int sum = 0;
+    for (int i = lo; i < hi; ++i) sum += a[i];
+    int tot;
+    int run = block_scan_incl(sum, wsum, &tot) - sum;
+    for (int i = lo; i < hi; ++i) {
+        const int v = a[i];
+        a[i] = run;
+        run += v;
+    }
+    if (threadIdx.x == 0) *total = tot;
+}
+
 int mvs_exclusive_scan_i32(int32_t* a, int64_t n, int64_t* tile_scratch, int64_t* total, cudaStream_t s) {
     if (n == 0) {
         MVS_CUDA_CHECK(cudaMemsetAsync(total, 0, sizeof(int64_t), s));
+        return MVS_OK;
+    }
+    if (n <= MVS_SCAN_SMALL_MAX) {
+        scan_small<<<1, 1024, 0, s>>>(a, (int)n, (int)((n + 1023) / 1024), total);
+        MVS_CUDA_CHECK(cudaGetLastError());
         return MVS_OK;
     }
     const int T = (int)((n + 1023) / 1024);

@@ -26,9 +26,15 @@ class DeviceBackend:
         self.scale, self.bound, self.min_ncc, self.wid = float(scale), int(bound), float(min_ncc), int(wid)
         self.rec_bytes = self.lib.mvs_record_bytes(ctx._h)
         self.device = torch.device("cuda", ctx.device)
+        if float(cell_size) != int(cell_size) or int(cell_size) < 1:
+            raise MvsError("the device cell table needs an integer cell_size >= 1 (got %r)" % (cell_size,))
+        cell_size = int(cell_size)
         tab = None
         if table is not None:
             tab = np.ascontiguousarray(np.asarray(table, dtype=np.uint8))
+            want = (ctx.V, -(-(ctx.W - 1) // cell_size), -(-(ctx.H - 1) // cell_size))   # MVS2.py:88
+            if tab.shape != want:
+                raise MvsError("cell table has shape %r, the device grid for cell_size %d is %r" % (tab.shape, cell_size, want))
         _check(self.lib.mvs_cells_init(ctx._h, int(cell_size), C.c_void_p(tab.ctypes.data) if tab is not None else None),
                "mvs_cells_init")
         cs, wc, hc = C.c_int(), C.c_int(), C.c_int()
@@ -119,6 +125,85 @@ class DeviceBackend:
             _check(self.lib.mvs_records_expand(self.ctx._h, self.WIRE_COMPACT, C.c_void_p(wire.data_ptr()), total,
                                                C.c_void_p(full.data_ptr()), self._stream()), "mvs_records_expand")
         return full[:total], counts
+
+    # -- the whole expansion in one C call (mvs_expand_run) ---------------------------------------
+    def exchange_setup(self, capacity, world, group):
+        """Symmetric-memory inbox (minimal wire, two parity halves) + barrier flags for the fused multi-GPU
+        rounds.  Collective over ``group``.  Raises when symmetric memory / peer access is unavailable."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        t = self.torch
+        nbytes = int(self.lib.mvs_exchange_bytes(self.ctx._h, world, capacity))
+        inbox = symm_mem.empty(nbytes, dtype=t.uint8, device=self.device)
+        flags = symm_mem.empty(world, dtype=t.int64, device=self.device)
+        flags.zero_()
+        h = symm_mem.rendezvous(inbox, group)
+        h2 = symm_mem.rendezvous(flags, group)
+        t.cuda.synchronize(self.device)
+        dist.barrier(group=group)                                 # every rank's flags are zero before the first device barrier
+        self._xchg = dict(inbox=inbox, flags=flags, h=h, h2=h2, cap=int(capacity), world=world,
+                          inbox_tab=(C.c_void_p * world)(*[int(x) for x in h.buffer_ptrs]),
+                          flag_tab=(C.c_void_p * world)(*[int(x) for x in h2.buffer_ptrs]))
+        return self._xchg
+
+    def expand_run(self, seeds_dev, max_rounds=None, max_iterations=None, max_patches=None, rank=0, world=1, timing=False):
+        """All rounds in one call.  Returns (stats: list of dict, n_patches); the accepted records stay in the
+        context (expand_result).  With world > 1 call exchange_setup first (on every rank)."""
+        prm = _lib.ExpandParams()
+        prm.min_ncc, prm.scale, prm.wid, prm.bound = self.min_ncc, self.scale, self.wid, self.bound
+        prm.max_rounds = -1 if max_rounds is None else int(max_rounds)
+        prm.max_iterations = -1 if max_iterations is None else int(max_iterations)
+        prm.max_patches = -1 if max_patches is None else int(max_patches)
+        prm.rank, prm.world = int(rank), int(world)
+        prm.timing = 1 if timing else 0
+        if world > 1:
+            x = self._xchg
+            prm.peer_inbox = C.cast(x["inbox_tab"], C.c_void_p)
+            prm.peer_flags = C.cast(x["flag_tab"], C.c_void_p)
+            prm.capacity = x["cap"]
+        max_stats = 4096
+        stats = (_lib.RoundStat * max_stats)()
+        n_rounds, n_patches = C.c_int(0), C.c_int64(0)
+        n = int(seeds_dev.shape[0])
+        _check(self.lib.mvs_expand_run(self.ctx._h, C.c_void_p(seeds_dev.data_ptr()) if n else None, n, C.byref(prm),
+                                       C.cast(stats, C.c_void_p), max_stats, C.byref(n_rounds), C.byref(n_patches),
+                                       self._stream()), "mvs_expand_run")
+        out = [dict(frontier=int(st.frontier), candidates=int(st.candidates), passed=int(st.passed),
+                    accepted=int(st.accepted), ms=float(st.ms)) for st in stats[:min(n_rounds.value, max_stats)]]
+        return out, int(n_patches.value)
+
+    def expand_result(self, offset, n):
+        """Accepted patch records [offset, offset+n) of the last expand_run as a NumPy structured array."""
+        out = np.empty(n, dtype=rec_dtype(self.ctx.V))
+        if n:
+            _check(self.lib.mvs_expand_result(self.ctx._h, C.c_void_p(out.ctypes.data), int(offset), int(n), 0, self._stream()),
+                   "mvs_expand_result")
+        return out
+
+    # -- seed stage and outlier filter --------------------------------------------------------------
+    def seed_stage(self, obs, offsets, P, min_ncc=0.4):
+        """mvs_seed_stage: SfM tracks (flat observation list) -> seed patch records (NumPy), in track order.
+        The records' ``index`` is the candidate number inside the flat (track, k >= 1) candidate list."""
+        obs = np.ascontiguousarray(np.asarray(obs, dtype=np.float64).reshape(-1, 3))
+        offsets = np.ascontiguousarray(np.asarray(offsets, dtype=np.int64))
+        P = np.ascontiguousarray(np.asarray(P, dtype=np.float64).reshape(self.ctx.V, 12))
+        nt = len(offsets) - 1
+        seeds = self.empty(max(nt, 1))
+        n = C.c_int64(0)
+        _check(self.lib.mvs_seed_stage(self.ctx._h, nt, C.c_void_p(offsets.ctypes.data), C.c_void_p(obs.ctypes.data),
+                                       C.c_void_p(P.ctypes.data), float(min_ncc), self.wid, self.bound,
+                                       C.c_void_p(seeds.data_ptr()), C.addressof(n), self._stream()), "mvs_seed_stage")
+        return self.to_host(seeds[: n.value])
+
+    def filter(self, records_np):
+        """mvs_cells_filter on records in insertion order -> (removed bool [n], n_removed, n_empty_cells)."""
+        n = len(records_np)
+        dev = self.to_device(records_np) if n else self.empty(1)
+        removed = self.torch.zeros(max(n, 1), dtype=self.torch.uint8, device=self.device)
+        counts = (C.c_int64 * 2)()
+        _check(self.lib.mvs_cells_filter(self.ctx._h, C.c_void_p(dev.data_ptr()), n, C.c_void_p(removed.data_ptr()),
+                                         C.cast(counts, C.c_void_p), self._stream()), "mvs_cells_filter")
+        return removed[:n].cpu().numpy().astype(bool), int(counts[0]), int(counts[1])
 
     def commit(self, records):
         n = records.shape[0]

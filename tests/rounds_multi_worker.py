@@ -1,8 +1,8 @@
 """Worker of tests/test_rounds_multi_gpu.py: run under torchrun, one process per GPU.  Every rank runs the
-round driver with the candidates sharded over the ranks -- once with the NCCL all-gather of accepted
-records, once with the exchange fused into the compaction (P2P stores into symmetric-memory inboxes,
-compact wire records expanded on the receiver) -- and, in a third context, unsharded; the accepted records
-and the cell tables must be identical in all three."""
+rounds with the candidates sharded over the ranks -- with the NCCL all-gather of accepted records, with the
+exchange fused into the compaction (P2P stores of 64-byte wire records), with the fused pipeline of
+mvs_expand_run (minimal wire + device barrier + commit from the wire) -- and, in another context,
+unsharded; the accepted records and the cell tables must be identical in all of them."""
 import os
 import sys
 
@@ -33,9 +33,17 @@ def main():
             drv = RoundDriver(be, rank=r, world=w, exchange=ex)
             acc = drv.run(be.to_device(seeds), max_rounds=6)
             out[name] = (np.concatenate([be.to_host(a) for a in acc]) if acc else None, be.table(), drv.stats)
+    # the fused pipeline (mvs_expand_run): minimal wire published into every GPU's symmetric-memory inbox over
+    # NVLink stores, one device-side flag barrier per round, commit from the wire -- sharded over the ranks
+    with mvs_b200.MvsContext(s["rgb"], s["K"], s["R"], s["t"], Rrt=s["Rrt"], device=local) as ctx:
+        be = DeviceBackend(ctx, cell_size=2, scale=float(e["scale"]), bound=int(e["bound"]), table=e["table_before"])
+        be.exchange_setup(4096, world, dist.group.WORLD)
+        stats, n = be.expand_run(be.to_device(seeds), max_rounds=6, rank=rank, world=world)
+        fused = (be.expand_result(0, n), be.table(), stats)
     a, b, p = out["sharded"], out["single"], out["p2p"]
     same = (a[0] is not None and b[0] is not None and a[0].tobytes() == b[0].tobytes() and np.array_equal(a[1], b[1]) and
-            p[0] is not None and p[0].tobytes() == b[0].tobytes() and np.array_equal(p[1], b[1]))
+            p[0] is not None and p[0].tobytes() == b[0].tobytes() and np.array_equal(p[1], b[1]) and
+            fused[0].tobytes() == b[0].tobytes() and np.array_equal(fused[1], b[1]))
     shards = [st["shard"] for st in a[2]]
     ok = torch.tensor([int(same and len(a[0]) > 50)], device="cuda")
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)

@@ -153,3 +153,56 @@ def test_mode_b_spec_prefers_true_surface():
     assert best[0] == 1 and avg[0] == 0.9
     best, _ = mode_b.select_best(np.array([0.5, 0.9]), np.array([1, 2]), 3, 2)
     assert best[0] == -1
+
+
+def test_filter_oracle_reproduces_the_reference(golden):
+    """oracle/filter.py against CellTable.filter_out_outlier run by the reference itself
+    (oracle/make_golden.py --filter: 1 735 patches, 351 removed, order dependence across views)."""
+    from oracle import filter as F
+    g = golden("filter12")
+    removed, n_empty = F.filter_out_outlier(g["table"], int(g["cell_size"]), g["c"], g["n"], g["avg"], g["vis"], g["xy"])
+    assert np.array_equal(removed, g["removed"]) and n_empty == 0
+    # the surviving Q lists of the reference contain exactly the survivors that see the list's view
+    alive = ~removed
+    ci, cj = np.floor(g["xy"][:, 0] / int(g["cell_size"])).astype(int), np.floor(g["xy"][:, 1] / int(g["cell_size"])).astype(int)
+    for k, (v, i, j) in enumerate(g["q_keys"]):
+        members = g["q_members"][g["q_offsets"][k]:g["q_offsets"][k + 1]]
+        want = np.nonzero(alive & g["vis"][:, v] & (ci == i) & (cj == j))[0]
+        assert np.array_equal(members, want)
+
+
+def test_triangulation_oracle_matches_cv2(golden):
+    """oracle/triangulate.py (restated OpenCV DLT + one-sided Jacobi SVD) against cv2.triangulatePoints on
+    noisy correspondences, and the nearest-first seed pick against a Python heap (MVS2.py:14,253-260)."""
+    cv2 = pytest.importorskip("cv2")
+    import heapq
+    from oracle import triangulate as T
+    s = golden("dino12_scores")
+    K, R, t = s["K"], s["R"], s["t"]
+    V = len(K)
+    P = np.stack([K[v] @ np.concatenate((R[v], t[v].reshape(3, 1)), axis=1) for v in range(V)])
+    rng = np.random.default_rng(2)
+    n = 120
+    X = rng.uniform([-0.02, 0.02, -0.02], [0.05, 0.1, 0.05], (n, 3))
+    va = rng.integers(0, V, n)
+    vb = (va + rng.integers(1, V, n)) % V
+    h = lambda v: (P[v] @ np.concatenate([X, np.ones((n, 1))], axis=1)[:, :, None])[:, :, 0]
+    xa = h(va)[:, :2] / h(va)[:, 2:3] + rng.normal(0, 0.3, (n, 2))
+    xb = h(vb)[:, :2] / h(vb)[:, 2:3] + rng.normal(0, 0.3, (n, 2))
+    got = T.triangulate(P[va], P[vb], xa, xb)
+    for i in range(n):
+        un = cv2.triangulatePoints(P[va[i]], P[vb[i]], xa[i].reshape(2, 1), xb[i].reshape(2, 1)).T[0]
+        assert np.abs(un[:3] / un[3] - got[i, :3] / got[i, 3]).max() < 1e-11
+    track = np.sort(rng.integers(0, 20, n))
+    dist, cnt, ref = rng.random(n), rng.integers(0, 6, n), rng.integers(0, V, n)
+    sel = T.seed_select(track, dist, X, ref, cnt, 3, 20)
+    for ti in range(20):
+        heap = [((dist[i], X[i, 0], X[i, 1], X[i, 2], ref[i]), i) for i in np.nonzero(track == ti)[0]]
+        heapq.heapify(heap)
+        pick = -1
+        while heap:
+            _, i = heapq.heappop(heap)
+            if cnt[i] >= 3:
+                pick = i
+                break
+        assert sel[ti] == pick
