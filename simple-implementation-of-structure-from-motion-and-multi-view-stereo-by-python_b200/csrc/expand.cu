@@ -46,88 +46,105 @@ __device__ __forceinline__ unsigned long long claim_value(unsigned epoch, long l
     return ((unsigned long long)epoch << 40) | (unsigned long long)((1ll << 40) - 1 - slot);
 }
 
-// pass 0: claim cells; pass 1: count surviving slots; pass 2: emit candidates
+// pass 0: claim cells; pass 1: count surviving slots; pass 2: emit candidates.
+// ONE WARP per frontier patch, lanes span its views (lane v handles view v, v + 32, ...): the reference's
+// loop order (view ascending, then the four diagonals, MVS2.py:328-332) is the lane order, so the number of
+// surviving slots before a lane's is a warp prefix sum and the candidates of a patch land in ascending slot
+// order without any per-thread serial walk over the visible set.
 template <int PASS>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
     expand_slots(const uint8_t* __restrict__ frontier, int64_t F, int rec_bytes, int V, int cs, int wc, int hc,
                  const uint8_t* __restrict__ cells, unsigned long long* __restrict__ claim, unsigned epoch,
                  int32_t* __restrict__ counts /*[F]*/, const CamGeom* __restrict__ geom, int64_t* __restrict__ cand_slot,
                  int64_t* __restrict__ cand_parent, double* __restrict__ cand_c, double* __restrict__ cand_n,
                  int32_t* __restrict__ cand_ref, int32_t* __restrict__ cand_px, const int64_t* __restrict__ d_F = nullptr,
                  int64_t F_clamp = 0) {
-    const int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int64_t f = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     if (d_F) {
         // frontier size still on the device (the commit that produced it has not been read back): the grid
-        // covers an upper bound `F`, threads past the real size only zero their count
+        // covers an upper bound `F`, warps past the real size only zero their count
         const int64_t Fd = *d_F < F_clamp ? *d_F : F_clamp;
         if (f >= Fd) {
-            if (PASS == 1 && f < F) counts[f] = 0;
+            if (PASS == 1 && f < F && lane == 0) counts[f] = 0;
             return;
         }
     }
     if (f >= F) return;
     const mvs_patch_record* p = rec_at(frontier, f, rec_bytes);
     const uint64_t* vis = rec_vis(p);
-    int ci, cj;
-    int n_live = 0;
-    int64_t out = (PASS == 2) ? (int64_t)counts[f] : 0;
-    if (which_cell(p->xy[0], p->xy[1], cs, ci, cj)) {
-        const int mw = (V + 63) >> 6;
-        for (int w = 0; w < mw; ++w) {
-            uint64_t bits = vis[w];
-            while (bits) {
-                const int v = w * 64 + __ffsll((long long)bits) - 1;
-                bits &= bits - 1;
-                if (v >= V) break;
-                for (int k = 0; k < 4; ++k) {
-                    const int ti = ci + c_di[k], tj = cj + c_dj[k];
-                    if (ti < 0 || ti >= wc || tj < 0 || tj >= hc) continue;              // is_vacant: out of range
-                    const int64_t cell = ((int64_t)v * wc + ti) * hc + tj;
-                    if (!cells[cell]) continue;                                          // MVS2.py:333
-                    const long long slot = ((long long)f * V + v) * 4 + k;
-                    const unsigned long long mine = claim_value(epoch, slot);
-                    if (PASS == 0) {
-                        atomicMax(claim + cell, mine);
-                        continue;
-                    }
-                    if (claim[cell] != mine) continue;                                   // a lower slot tests this cell
-                    if (PASS == 1) {
-                        ++n_live;
-                        continue;
-                    }
-                    // ---- PASS 2: candidate geometry, MVS2.py:334-358 -----------------------------
-                    const CamGeom& g = geom[v];
-                    const int di = c_di[k];
-                    const double u = xmul((double)cs, xadd((double)(ci + di), 0.5));
-                    const double vv = xmul((double)cs, xadd((double)(cj + di), 0.5));      // sic: di on both axes
-                    const double a0 = xsub(u, g.cx), a1 = xsub(vv, g.cy), a2 = xdiv(xadd(g.fx, g.fy), 2.0);
-                    // R^T a + C  (sic: "+ C", MVS2.py:353)
-                    const double P0 = xadd(dot3(g.rf[0], g.rf[3], g.rf[6], a0, a1, a2), g.C[0]);
-                    const double P1 = xadd(dot3(g.rf[1], g.rf[4], g.rf[7], a0, a1, a2), g.C[1]);
-                    const double P2 = xadd(dot3(g.rf[2], g.rf[5], g.rf[8], a0, a1, a2), g.C[2]);
-                    const double nrm = sqrt(dot3(P0, P1, P2, P0, P1, P2));
-                    const double d0 = xdiv(P0, nrm), d1 = xdiv(P1, nrm), d2 = xdiv(P2, nrm);
-                    // ray_plane_intersection (MVS2.py:302-306) with origin O = C
-                    const double dot_out = dot3(d0, d1, d2, p->n[0], p->n[1], p->n[2]);
-                    const double w0 = xsub(p->c[0], g.C[0]), w1 = xsub(p->c[1], g.C[1]), w2 = xsub(p->c[2], g.C[2]);
-                    const double tpar = xdiv(dot3(w0, w1, w2, p->n[0], p->n[1], p->n[2]), dot_out);
-                    const double X0 = xadd(g.C[0], xmul(tpar, d0)), X1 = xadd(g.C[1], xmul(tpar, d1)),
-                                 X2 = xadd(g.C[2], xmul(tpar, d2));
-                    const double q0 = xsub(g.C[0], X0), q1 = xsub(g.C[1], X1), q2 = xsub(g.C[2], X2);
-                    const double dist = sqrt(dot3(q0, q1, q2, q0, q1, q2));
-                    cand_slot[out] = slot;
-                    cand_parent[out] = f;
-                    cand_c[3 * out] = X0; cand_c[3 * out + 1] = X1; cand_c[3 * out + 2] = X2;
-                    cand_n[3 * out] = xdiv(q0, dist); cand_n[3 * out + 1] = xdiv(q1, dist); cand_n[3 * out + 2] = xdiv(q2, dist);
-                    cand_ref[out] = v;
-                    cand_px[2 * out] = (int)u;
-                    cand_px[2 * out + 1] = (int)vv;
-                    ++out;
+    int ci = 0, cj = 0;
+    const bool ok = which_cell(p->xy[0], p->xy[1], cs, ci, cj);
+    int64_t base = (PASS == 2) ? (int64_t)counts[f] : 0;          // candidates of this patch emitted so far
+    int total = 0;
+    for (int v0 = 0; v0 < V; v0 += 32) {
+        const int v = v0 + lane;
+        const bool seen = ok && v < V && ((vis[v >> 6] >> (v & 63)) & 1ull);
+        unsigned live = 0u;                                       // bit k: diagonal k of view v survives
+        if (seen) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int ti = ci + c_di[k], tj = cj + c_dj[k];
+                if (ti < 0 || ti >= wc || tj < 0 || tj >= hc) continue;                  // is_vacant: out of range
+                const int64_t cell = ((int64_t)v * wc + ti) * hc + tj;
+                if (!cells[cell]) continue;                                              // MVS2.py:333
+                const long long slot = ((long long)f * V + v) * 4 + k;
+                const unsigned long long mine = claim_value(epoch, slot);
+                if (PASS == 0) {
+                    atomicMax(claim + cell, mine);
+                    continue;
                 }
+                if (claim[cell] == mine) live |= 1u << k;                                // else a lower slot tests this cell
             }
         }
+        if (PASS == 0) continue;
+        const int n_live = __popc(live);
+        int incl = n_live;
+#pragma unroll
+        for (int sft = 1; sft < 32; sft <<= 1) {
+            const int y = __shfl_up_sync(FULL, incl, sft);
+            if (lane >= sft) incl += y;
+        }
+        const int chunk_total = __shfl_sync(FULL, incl, 31);
+        if (PASS == 2 && live) {
+            int64_t out = base + (incl - n_live);
+            const CamGeom& g = geom[v];
+#pragma unroll 1
+            for (int k = 0; k < 4; ++k) {
+                if (!((live >> k) & 1u)) continue;
+                // ---- candidate geometry, MVS2.py:334-358 -----------------------------
+                const int di = c_di[k];
+                const double u = xmul((double)cs, xadd((double)(ci + di), 0.5));
+                const double vv = xmul((double)cs, xadd((double)(cj + di), 0.5));      // sic: di on both axes
+                const double a0 = xsub(u, g.cx), a1 = xsub(vv, g.cy), a2 = xdiv(xadd(g.fx, g.fy), 2.0);
+                // R^T a + C  (sic: "+ C", MVS2.py:353)
+                const double P0 = xadd(dot3(g.rf[0], g.rf[3], g.rf[6], a0, a1, a2), g.C[0]);
+                const double P1 = xadd(dot3(g.rf[1], g.rf[4], g.rf[7], a0, a1, a2), g.C[1]);
+                const double P2 = xadd(dot3(g.rf[2], g.rf[5], g.rf[8], a0, a1, a2), g.C[2]);
+                const double nrm = sqrt(dot3(P0, P1, P2, P0, P1, P2));
+                const double d0 = xdiv(P0, nrm), d1 = xdiv(P1, nrm), d2 = xdiv(P2, nrm);
+                // ray_plane_intersection (MVS2.py:302-306) with origin O = C
+                const double dot_out = dot3(d0, d1, d2, p->n[0], p->n[1], p->n[2]);
+                const double w0 = xsub(p->c[0], g.C[0]), w1 = xsub(p->c[1], g.C[1]), w2 = xsub(p->c[2], g.C[2]);
+                const double tpar = xdiv(dot3(w0, w1, w2, p->n[0], p->n[1], p->n[2]), dot_out);
+                const double X0 = xadd(g.C[0], xmul(tpar, d0)), X1 = xadd(g.C[1], xmul(tpar, d1)),
+                             X2 = xadd(g.C[2], xmul(tpar, d2));
+                const double q0 = xsub(g.C[0], X0), q1 = xsub(g.C[1], X1), q2 = xsub(g.C[2], X2);
+                const double dist = sqrt(dot3(q0, q1, q2, q0, q1, q2));
+                cand_slot[out] = ((long long)f * V + v) * 4 + k;
+                cand_parent[out] = f;
+                cand_c[3 * out] = X0; cand_c[3 * out + 1] = X1; cand_c[3 * out + 2] = X2;
+                cand_n[3 * out] = xdiv(q0, dist); cand_n[3 * out + 1] = xdiv(q1, dist); cand_n[3 * out + 2] = xdiv(q2, dist);
+                cand_ref[out] = v;
+                cand_px[2 * out] = (int)u;
+                cand_px[2 * out + 1] = (int)vv;
+                ++out;
+            }
+        }
+        base += chunk_total;
+        total += chunk_total;
     }
-    if (PASS == 1) counts[f] = n_live;
+    if (PASS == 1 && lane == 0) counts[f] = total;
 }
 
 // accept gate of MVS2.py:369 without the visible_ct clause (applied by the compaction):
@@ -293,12 +310,12 @@ extern "C" int mvs_round_generate(mvs_ctx* ctx, const void* frontier, int64_t F,
     if ((rc = mvs_ensure((void**)&ctx->d_scan, &ctx->scan_bytes, sizeof(int64_t) * ((F + 1023) / 1024 + 2), "scan")) != MVS_OK) return rc;
     ctx->epoch++;
     const int rb = rec_bytes_of(ctx);
-    const unsigned blocks = (unsigned)((F + 127) / 128);
+    const unsigned blocks = (unsigned)((F + 7) / 8);                 // one warp per frontier patch
     int64_t* d_total = ctx->d_scan + (F + 1023) / 1024;
-    expand_slots<0><<<blocks, 128, 0, s>>>((const uint8_t*)frontier, F, rb, ctx->V, ctx->cell_size, ctx->wc, ctx->hc, ctx->d_cells,
+    expand_slots<0><<<blocks, 256, 0, s>>>((const uint8_t*)frontier, F, rb, ctx->V, ctx->cell_size, ctx->wc, ctx->hc, ctx->d_cells,
                                           ctx->d_claim, ctx->epoch, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
                                           nullptr, nullptr);
-    expand_slots<1><<<blocks, 128, 0, s>>>((const uint8_t*)frontier, F, rb, ctx->V, ctx->cell_size, ctx->wc, ctx->hc, ctx->d_cells,
+    expand_slots<1><<<blocks, 256, 0, s>>>((const uint8_t*)frontier, F, rb, ctx->V, ctx->cell_size, ctx->wc, ctx->hc, ctx->d_cells,
                                           ctx->d_claim, ctx->epoch, ctx->d_counts, nullptr, nullptr, nullptr, nullptr, nullptr,
                                           nullptr, nullptr);
     ctx->launches += 2;
@@ -311,7 +328,7 @@ extern "C" int mvs_round_generate(mvs_ctx* ctx, const void* frontier, int64_t F,
     if (M >= (1ll << 31)) { mvs_set_error("more than 2^31 candidates in one round"); return MVS_ERR_ARG; }
     if (M > 0) {
         if ((rc = ensure_candidates(ctx, M)) != MVS_OK) return rc;
-        expand_slots<2><<<blocks, 128, 0, s>>>((const uint8_t*)frontier, F, rb, ctx->V, ctx->cell_size, ctx->wc, ctx->hc,
+        expand_slots<2><<<blocks, 256, 0, s>>>((const uint8_t*)frontier, F, rb, ctx->V, ctx->cell_size, ctx->wc, ctx->hc,
                                               ctx->d_cells, ctx->d_claim, ctx->epoch, ctx->d_counts, ctx->d_geom, ctx->cand_slot,
                                               ctx->cand_parent, ctx->cand_c, ctx->cand_n, ctx->cand_ref, ctx->cand_px);
         ctx->launches++;
@@ -473,12 +490,12 @@ static int generate_count(mvs_ctx* ctx, const void* frontier, int64_t F_upper, c
     if ((rc = mvs_ensure((void**)&ctx->d_scan, &ctx->scan_bytes, sizeof(int64_t) * ((F_upper + 1023) / 1024 + 2), "scan")) != MVS_OK) return rc;
     ctx->epoch++;
     const int rb = rec_bytes_of(ctx);
-    const unsigned blocks = (unsigned)((F_upper + 127) / 128);
+    const unsigned blocks = (unsigned)((F_upper + 7) / 8);           // one warp per frontier patch
     int64_t* d_total = ctx->d_scan + (F_upper + 1023) / 1024;
-    expand_slots<0><<<blocks, 128, 0, s>>>((const uint8_t*)frontier, F_upper, rb, ctx->V, ctx->cell_size, ctx->wc, ctx->hc,
+    expand_slots<0><<<blocks, 256, 0, s>>>((const uint8_t*)frontier, F_upper, rb, ctx->V, ctx->cell_size, ctx->wc, ctx->hc,
                                           ctx->d_cells, ctx->d_claim, ctx->epoch, nullptr, nullptr, nullptr, nullptr, nullptr,
                                           nullptr, nullptr, nullptr, d_F, F_clamp);
-    expand_slots<1><<<blocks, 128, 0, s>>>((const uint8_t*)frontier, F_upper, rb, ctx->V, ctx->cell_size, ctx->wc, ctx->hc,
+    expand_slots<1><<<blocks, 256, 0, s>>>((const uint8_t*)frontier, F_upper, rb, ctx->V, ctx->cell_size, ctx->wc, ctx->hc,
                                           ctx->d_cells, ctx->d_claim, ctx->epoch, ctx->d_counts, nullptr, nullptr, nullptr,
                                           nullptr, nullptr, nullptr, nullptr, d_F, F_clamp);
     ctx->launches += 2;
@@ -554,7 +571,7 @@ extern "C" int mvs_expand_run(mvs_ctx* ctx, const void* seeds, int64_t n_seeds, 
                 return rc;
             if (frontier_in_out) frontier = ctx->d_out + frontier_off * rb;   // the buffer may have moved
             // ---- candidates of this round
-            expand_slots<2><<<(unsigned)((F + 127) / 128), 128, 0, s>>>(frontier, F, rb, ctx->V, ctx->cell_size, ctx->wc, ctx->hc,
+            expand_slots<2><<<(unsigned)((F + 7) / 8), 256, 0, s>>>(frontier, F, rb, ctx->V, ctx->cell_size, ctx->wc, ctx->hc,
                                                                         ctx->d_cells, ctx->d_claim, ctx->epoch, ctx->d_counts,
                                                                         ctx->d_geom, ctx->cand_slot, ctx->cand_parent, ctx->cand_c,
                                                                         ctx->cand_n, ctx->cand_ref, ctx->cand_px);

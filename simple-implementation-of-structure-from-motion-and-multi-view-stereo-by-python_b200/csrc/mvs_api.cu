@@ -138,8 +138,7 @@ extern "C" int mvs_create(mvs_ctx** out, int device, int V, int H, int W, const 
     ctx->maps_wid = -1;
     int rc = MVS_OK;
     const size_t gray_bytes = (size_t)ctx->rowpitch * H + 256;
-    const size_t rgb_bytes = (size_t)V * H * W * 3;
-    uint8_t* d_rgb = nullptr;
+    uint8_t* d_stage2[2] = {nullptr, nullptr};
     CamProj* hp = (CamProj*)malloc(sizeof(CamProj) * V);
     CamGeom* hg = (CamGeom*)malloc(sizeof(CamGeom) * V);
     ctx->h_rrt = (double*)malloc(sizeof(double) * 9 * V);
@@ -185,20 +184,55 @@ extern "C" int mvs_create(mvs_ctx** out, int device, int V, int H, int W, const 
     if (rgb_on_device) {
         // the caller's stream ordering is unknown: make its writes visible first
         if (cudaDeviceSynchronize() != cudaSuccess) { rc = MVS_ERR_CUDA; goto fail; }
-        rc = mvs_launch_gray(ctx, rgb, ctx->own_stream);
+        rc = mvs_launch_gray(ctx, rgb, 0, V, ctx->own_stream);
     } else {
-        if (cudaMalloc(&d_rgb, rgb_bytes) != cudaSuccess) {
-            mvs_set_error("mvs_create: cudaMalloc of %zu RGB bytes failed", rgb_bytes);
-            cudaGetLastError();
+        // Load path (main.py:7-20 hands over pageable NumPy images): chunks of whole views go through two
+        // PINNED host buffers and two device staging buffers -- the CPU fills pinned buffer k+1 while the DMA
+        // engine uploads chunk k on a copy stream and prep_gray4 converts chunk k-1 on the compute stream.
+        // No full-size RGB copy ever exists on the device (6.4 GB for 256 x 4K).
+        const size_t view_bytes = (size_t)H * W * 3;
+        size_t target = 32u << 20;                            // ~32 MB per chunk
+        if (const char* e = getenv("MVS_UPLOAD_CHUNK_MB")) {
+            const long mb = atol(e);
+            if (mb > 0) target = (size_t)mb << 20;
+        }
+        int per = (int)(target / view_bytes);
+        per = per < 1 ? 1 : (per > V ? V : per);
+        const size_t chunk_bytes = view_bytes * per;
+        uint8_t* h_pin[2] = {nullptr, nullptr};
+        cudaStream_t copy_s = nullptr;
+        cudaEvent_t up[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr};
+        bool ok = cudaStreamCreateWithFlags(&copy_s, cudaStreamNonBlocking) == cudaSuccess;
+        for (int i = 0; i < 2 && ok; ++i)
+            ok = cudaMallocHost(&h_pin[i], chunk_bytes) == cudaSuccess && cudaMalloc(&d_stage2[i], chunk_bytes) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&up[i], cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming) == cudaSuccess;
+        if (!ok) {
+            mvs_set_error("mvs_create: staging allocation (2 x %zu bytes pinned + device) failed: %s", chunk_bytes,
+                          cudaGetErrorString(cudaGetLastError()));
             rc = MVS_ERR_NOMEM;
-            goto fail;
         }
-        if (cudaMemcpyAsync(d_rgb, rgb, rgb_bytes, cudaMemcpyHostToDevice, ctx->own_stream) != cudaSuccess) {
-            mvs_set_error("mvs_create: RGB upload failed: %s", cudaGetErrorString(cudaGetLastError()));
-            rc = MVS_ERR_CUDA;
-            goto fail;
+        for (int v0 = 0, k = 0; rc == MVS_OK && v0 < V; v0 += per, ++k) {
+            const int nv = V - v0 < per ? V - v0 : per;
+            const int sl = k & 1;
+            if (k >= 2 && cudaEventSynchronize(done[sl]) != cudaSuccess) { rc = MVS_ERR_CUDA; break; }   // slot free again
+            memcpy(h_pin[sl], rgb + (size_t)v0 * view_bytes, view_bytes * nv);
+            if (cudaMemcpyAsync(d_stage2[sl], h_pin[sl], view_bytes * nv, cudaMemcpyHostToDevice, copy_s) != cudaSuccess ||
+                cudaEventRecord(up[sl], copy_s) != cudaSuccess || cudaStreamWaitEvent(ctx->own_stream, up[sl], 0) != cudaSuccess) {
+                mvs_set_error("mvs_create: RGB upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+                rc = MVS_ERR_CUDA;
+                break;
+            }
+            if ((rc = mvs_launch_gray(ctx, d_stage2[sl], v0, nv, ctx->own_stream)) != MVS_OK) break;
+            if (cudaEventRecord(done[sl], ctx->own_stream) != cudaSuccess) { rc = MVS_ERR_CUDA; break; }
         }
-        rc = mvs_launch_gray(ctx, d_rgb, ctx->own_stream);
+        if (cudaStreamSynchronize(ctx->own_stream) != cudaSuccess && rc == MVS_OK) rc = MVS_ERR_CUDA;
+        for (int i = 0; i < 2; ++i) {
+            if (h_pin[i]) cudaFreeHost(h_pin[i]);
+            if (up[i]) cudaEventDestroy(up[i]);
+            if (done[i]) cudaEventDestroy(done[i]);
+        }
+        if (copy_s) cudaStreamDestroy(copy_s);
     }
     if (rc != MVS_OK) goto fail;
     if (cudaStreamSynchronize(ctx->own_stream) != cudaSuccess) {
@@ -206,13 +240,15 @@ extern "C" int mvs_create(mvs_ctx** out, int device, int V, int H, int W, const 
         rc = MVS_ERR_CUDA;
         goto fail;
     }
-    if (d_rgb) cudaFree(d_rgb);
+    for (int i = 0; i < 2; ++i)
+        if (d_stage2[i]) cudaFree(d_stage2[i]);
     free(hp);
     free(hg);
     *out = ctx;
     return MVS_OK;
 fail:
-    if (d_rgb) cudaFree(d_rgb);
+    for (int i = 0; i < 2; ++i)
+        if (d_stage2[i]) cudaFree(d_stage2[i]);
     free(hp);
     free(hg);
     mvs_destroy(ctx);

@@ -144,7 +144,7 @@ void mvs_set_error(const char* fmt, ...);
     } while (0)
 
 // kernels / launchers implemented in the .cu files
-int mvs_launch_gray(mvs_ctx* ctx, const uint8_t* d_rgb, cudaStream_t s);
+int mvs_launch_gray(mvs_ctx* ctx, const uint8_t* d_rgb, int v0, int nv, cudaStream_t s);
 int mvs_launch_unpack_gray(mvs_ctx* ctx, uint8_t* d_planar, cudaStream_t s);
 int mvs_launch_score_refexact(mvs_ctx* ctx, int64_t N, const double* c, const int32_t* ref, double thr, int wid,
                               uint64_t* vis, double* avg, int32_t* count, double* xy, float* ncc, cudaStream_t s);

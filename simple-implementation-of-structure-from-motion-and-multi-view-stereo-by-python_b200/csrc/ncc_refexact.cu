@@ -42,15 +42,16 @@ __device__ __forceinline__ uint32_t gray_px(uint32_t r, uint32_t g, uint32_t b) 
     return (r * 3735u + g * 19235u + b * 9798u + 16384u) >> 15;
 }
 
-__global__ void __launch_bounds__(256) prep_gray4(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ gray4, int V, int H,
-                                                  int W, int Gw, int64_t gstride, int64_t rowpitch) {
-    const int64_t total = (int64_t)H * Gw * V;
+__global__ void __launch_bounds__(256) prep_gray4(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ gray4, int v0, int nv,
+                                                  int H, int W, int Gw, int64_t gstride, int64_t rowpitch) {
+    // rgb holds the views [v0, v0 + nv) only (one upload chunk, or the whole stack)
+    const int64_t total = (int64_t)H * Gw * nv;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int v = (int)(i % V);
-        const int64_t rg = i / V;
+        const int vl = (int)(i % nv);
+        const int64_t rg = i / nv;
         const int g = (int)(rg % Gw);
         const int row = (int)(rg / Gw);
-        const uint8_t* src = rgb + (((int64_t)v * H + row) * W + g * 4) * 3;
+        const uint8_t* src = rgb + (((int64_t)vl * H + row) * W + g * 4) * 3;
         uint32_t out = 0;
         const int npx = min(4, W - g * 4);
         if (npx == 4 && ((reinterpret_cast<uintptr_t>(src) & 3) == 0)) {
@@ -65,18 +66,19 @@ __global__ void __launch_bounds__(256) prep_gray4(const uint8_t* __restrict__ rg
         } else {
             for (int k = 0; k < npx; ++k) out |= gray_px(src[3 * k], src[3 * k + 1], src[3 * k + 2]) << (8 * k);
         }
-        *reinterpret_cast<uint32_t*>(gray4 + row * rowpitch + g * gstride + 4 * v) = out;
+        *reinterpret_cast<uint32_t*>(gray4 + row * rowpitch + g * gstride + 4 * (v0 + vl)) = out;
     }
 }
 
-int mvs_launch_gray(mvs_ctx* ctx, const uint8_t* d_rgb, cudaStream_t s) {
+// convert the views [v0, v0 + nv) whose RGB pixels start at d_rgb
+int mvs_launch_gray(mvs_ctx* ctx, const uint8_t* d_rgb, int v0, int nv, cudaStream_t s) {
     const int Gw = (ctx->W + 3) >> 2;
-    const int64_t total = (int64_t)ctx->H * Gw * ctx->V;
+    const int64_t total = (int64_t)ctx->H * Gw * nv;
     int64_t blocks = (total + 255) / 256;
     const int64_t cap = (int64_t)ctx->sm_count * 16;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    prep_gray4<<<(int)blocks, 256, 0, s>>>(d_rgb, ctx->d_gray, ctx->V, ctx->H, ctx->W, Gw, ctx->gstride, ctx->rowpitch);
+    prep_gray4<<<(int)blocks, 256, 0, s>>>(d_rgb, ctx->d_gray, v0, nv, ctx->H, ctx->W, Gw, ctx->gstride, ctx->rowpitch);
     ctx->launches++;
     MVS_CUDA_CHECK(cudaGetLastError());
     return MVS_OK;
@@ -970,7 +972,7 @@ __global__ void __launch_bounds__(256, MINB)
 }
 
 #ifndef MVS_K6_MINB
-#define MVS_K6_MINB 3
+#define MVS_K6_MINB 2          // resident CTAs per SM: measured 0.364 ms (2: 128 registers, no spills) / 0.382 (3) / 0.470 (4) per 2^20 hypotheses
 #endif
 
 template <int WID, int GS, int MINB = MVS_K6_MINB>
@@ -1043,7 +1045,7 @@ static int launch_gather(mvs_ctx* ctx, const ScoreArgs& A, int64_t N, const uint
                 const char* e = getenv("MVS_K6_MINB");
                 mb = e ? atoi(e) : 0;
             }
-            if (mb == 2) return launch_gather6<5, 192, 2>(ctx, A, N, anchors, entries, s);
+            if (mb == 3) return launch_gather6<5, 192, 3>(ctx, A, N, anchors, entries, s);
             if (mb == 4) return launch_gather6<5, 192, 4>(ctx, A, N, anchors, entries, s);
             return launch_gather6<5, 192>(ctx, A, N, anchors, entries, s);
         }
