@@ -206,3 +206,30 @@ def test_triangulation_oracle_matches_cv2(golden):
                 pick = i
                 break
         assert sel[ti] == pick
+
+
+def test_ref_port_reproduces_the_reference(golden):
+    """oracle/ref_port.py -- the CPU arm bench.py times as cpu_baseline / --impl reference -- against the
+    reference's own outputs (dino12_scores): same visible sets, same averages.  It is the denominator of the
+    headline speed-up, so it is pinned like the oracle."""
+    from oracle import ref_port
+    d = golden("dino12_scores")
+    imgs = [d["rgb"][v] for v in range(d["rgb"].shape[0])]
+    import warnings
+    for tag, thr in (("t04", 0.4), ("t07", 0.7)):
+        for i in range(0, len(d["c"]), 23):
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                out, avg = ref_port.photo_consistency(imgs, d["K"], d["R"], d["t"], d["c"][i], int(d["ref"][i]), thr)
+            assert [h[0] for h in out] == list(np.nonzero(d[tag + "_vis"][i])[0]), (tag, i)
+            assert abs(avg - d[tag + "_avg"][i]) < 1e-12
+            for h in out:
+                assert abs(h[1] - d[tag + "_xy"][i, 0]) < 1e-9 and abs(h[2] - d[tag + "_xy"][i, 1]) < 1e-9
+    # the pooled entry point bench.py calls returns the same counts
+    pool = ref_port.Pool(d["rgb"], d["K"], d["R"], d["t"], 0.7, 2)
+    try:
+        idx = np.arange(0, len(d["c"]), 40)
+        res = pool.score(d["c"][idx], d["ref"][idx])
+    finally:
+        pool.close()
+    assert [r[0] for r in res] == [int(d["t07_vis"][i].sum()) for i in idx]

@@ -91,5 +91,32 @@ def test_dense_points_end_to_end(golden, built_lib, tmp_path, monkeypatch):
     assert dist.max() < 1e-6
     # colours are integer RGB triples taken from the images
     assert np.all(allp[:, 3:] == np.round(allp[:, 3:])) and allp[:, 3:].max() <= 255
-    # the expansion itself, replayed by the oracle from the same seeds
-    assert all(s["candidates"] > 0 for s in stats[:1])
+    # the expansion itself, replayed by the oracle from the drop-in's own seed patches: same accepted patches
+    # (centres bit-identical, in commit order) round after round, and the same final cell table
+    seeds_c = init[:, :3]
+    recs = MVS2.patch_expansion.last_records
+    assert len(recs) == sum(s["accepted"] for s in stats)
+    # re-derive the seeds as the oracle sees them: score the exported seed centres at 0.4 from their reference views
+    from oracle import triangulate as T
+    obs_flat, offs = MVS2._flatten_tracks(tracks, V)
+    sc = T.seed_candidates(obs_flat, offs, d["K"], d["R"], d["t"])
+    o = mode_a.score(gray, cams, sc["c"], sc["ref"], 0.4)
+    sel = T.seed_select(sc["track"], sc["dist"], sc["c"], sc["ref"], o["count"], 3, len(tracks))
+    sel = sel[sel >= 0]
+    assert len(sel) == len(init) and np.abs(sc["c"][sel] - seeds_c).max() < 1e-12
+    table = np.ones((V, 160, 120), dtype=bool)
+    ci, cj = np.floor(o["xy"][sel, 0] / 2).astype(int), np.floor(o["xy"][sel, 1] / 2).astype(int)
+    for k, i in enumerate(sel):
+        table[np.nonzero(o["vis"][i])[0], ci[k], cj[k]] = False                        # fill_with_point, MVS2.py:258-259
+    fr = dict(c=seeds_c.copy(), n=sc["n"][sel], vis=o["vis"][sel], xy=o["xy"][sel])
+    off = 0
+    for rnd, st in enumerate(stats):
+        cand, fr = expansion.expand_round(gray, cams, fr, table, float(e["scale"]), int(e["bound"]))
+        acc = cand["accepted"]
+        assert st["candidates"] == len(cand["slot"]) and st["accepted"] == int(acc.sum()), rnd
+        got = recs[off:off + st["accepted"]]
+        assert np.array_equal(got["index"], cand["slot"][acc])
+        assert np.abs(got["c"] - cand["c"][acc]).max() < 1e-12 if acc.any() else True
+        assert np.array_equal(records.unpack_vis(got["vis"], V), cand["vis"][acc])
+        off += st["accepted"]
+    assert stats[0]["candidates"] > 0 and off > 0
