@@ -107,37 +107,13 @@ __global__ void __launch_bounds__(256)
         }
         const int chunk_total = __shfl_sync(FULL, incl, 31);
         if (PASS == 2 && live) {
+            // only WHICH slots survive is decided here; their geometry is one thread per candidate (expand_geometry)
             int64_t out = base + (incl - n_live);
-            const CamGeom& g = geom[v];
-#pragma unroll 1
+#pragma unroll
             for (int k = 0; k < 4; ++k) {
                 if (!((live >> k) & 1u)) continue;
-                // ---- candidate geometry, MVS2.py:334-358 -----------------------------
-                const int di = c_di[k];
-                const double u = xmul((double)cs, xadd((double)(ci + di), 0.5));
-                const double vv = xmul((double)cs, xadd((double)(cj + di), 0.5));      // sic: di on both axes
-                const double a0 = xsub(u, g.cx), a1 = xsub(vv, g.cy), a2 = xdiv(xadd(g.fx, g.fy), 2.0);
-                // R^T a + C  (sic: "+ C", MVS2.py:353)
-                const double P0 = xadd(dot3(g.rf[0], g.rf[3], g.rf[6], a0, a1, a2), g.C[0]);
-                const double P1 = xadd(dot3(g.rf[1], g.rf[4], g.rf[7], a0, a1, a2), g.C[1]);
-                const double P2 = xadd(dot3(g.rf[2], g.rf[5], g.rf[8], a0, a1, a2), g.C[2]);
-                const double nrm = sqrt(dot3(P0, P1, P2, P0, P1, P2));
-                const double d0 = xdiv(P0, nrm), d1 = xdiv(P1, nrm), d2 = xdiv(P2, nrm);
-                // ray_plane_intersection (MVS2.py:302-306) with origin O = C
-                const double dot_out = dot3(d0, d1, d2, p->n[0], p->n[1], p->n[2]);
-                const double w0 = xsub(p->c[0], g.C[0]), w1 = xsub(p->c[1], g.C[1]), w2 = xsub(p->c[2], g.C[2]);
-                const double tpar = xdiv(dot3(w0, w1, w2, p->n[0], p->n[1], p->n[2]), dot_out);
-                const double X0 = xadd(g.C[0], xmul(tpar, d0)), X1 = xadd(g.C[1], xmul(tpar, d1)),
-                             X2 = xadd(g.C[2], xmul(tpar, d2));
-                const double q0 = xsub(g.C[0], X0), q1 = xsub(g.C[1], X1), q2 = xsub(g.C[2], X2);
-                const double dist = sqrt(dot3(q0, q1, q2, q0, q1, q2));
                 cand_slot[out] = ((long long)f * V + v) * 4 + k;
                 cand_parent[out] = f;
-                cand_c[3 * out] = X0; cand_c[3 * out + 1] = X1; cand_c[3 * out + 2] = X2;
-                cand_n[3 * out] = xdiv(q0, dist); cand_n[3 * out + 1] = xdiv(q1, dist); cand_n[3 * out + 2] = xdiv(q2, dist);
-                cand_ref[out] = v;
-                cand_px[2 * out] = (int)u;
-                cand_px[2 * out + 1] = (int)vv;
                 ++out;
             }
         }
@@ -145,6 +121,45 @@ __global__ void __launch_bounds__(256)
         total += chunk_total;
     }
     if (PASS == 1 && lane == 0) counts[f] = total;
+}
+
+// candidate geometry, MVS2.py:334-358, one thread per surviving slot (slot = (f*V + v)*4 + k)
+__global__ void __launch_bounds__(128)
+    expand_geometry(const uint8_t* __restrict__ frontier, int rec_bytes, int V, int cs, int64_t M,
+                    const int64_t* __restrict__ cand_slot, const CamGeom* __restrict__ geom, double* __restrict__ cand_c,
+                    double* __restrict__ cand_n, int32_t* __restrict__ cand_ref, int32_t* __restrict__ cand_px) {
+    const int64_t out = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (out >= M) return;
+    const long long slot = cand_slot[out];
+    const int k = (int)(slot & 3);
+    const int v = (int)((slot >> 2) % V);
+    const int64_t f = (slot >> 2) / V;
+    const mvs_patch_record* p = rec_at(frontier, f, rec_bytes);
+    int ci = 0, cj = 0;
+    which_cell(p->xy[0], p->xy[1], cs, ci, cj);                                        // a surviving slot has a valid cell
+    const CamGeom& g = geom[v];
+    const int di = c_di[k];
+    const double u = xmul((double)cs, xadd((double)(ci + di), 0.5));
+    const double vv = xmul((double)cs, xadd((double)(cj + di), 0.5));                  // sic: di on both axes (MVS2.py:334)
+    const double a0 = xsub(u, g.cx), a1 = xsub(vv, g.cy), a2 = xdiv(xadd(g.fx, g.fy), 2.0);
+    // R^T a + C  (sic: "+ C", MVS2.py:353)
+    const double P0 = xadd(dot3(g.rf[0], g.rf[3], g.rf[6], a0, a1, a2), g.C[0]);
+    const double P1 = xadd(dot3(g.rf[1], g.rf[4], g.rf[7], a0, a1, a2), g.C[1]);
+    const double P2 = xadd(dot3(g.rf[2], g.rf[5], g.rf[8], a0, a1, a2), g.C[2]);
+    const double nrm = sqrt(dot3(P0, P1, P2, P0, P1, P2));
+    const double d0 = xdiv(P0, nrm), d1 = xdiv(P1, nrm), d2 = xdiv(P2, nrm);
+    // ray_plane_intersection (MVS2.py:302-306) with origin O = C
+    const double dot_out = dot3(d0, d1, d2, p->n[0], p->n[1], p->n[2]);
+    const double w0 = xsub(p->c[0], g.C[0]), w1 = xsub(p->c[1], g.C[1]), w2 = xsub(p->c[2], g.C[2]);
+    const double tpar = xdiv(dot3(w0, w1, w2, p->n[0], p->n[1], p->n[2]), dot_out);
+    const double X0 = xadd(g.C[0], xmul(tpar, d0)), X1 = xadd(g.C[1], xmul(tpar, d1)), X2 = xadd(g.C[2], xmul(tpar, d2));
+    const double q0 = xsub(g.C[0], X0), q1 = xsub(g.C[1], X1), q2 = xsub(g.C[2], X2);
+    const double dist = sqrt(dot3(q0, q1, q2, q0, q1, q2));
+    cand_c[3 * out] = X0; cand_c[3 * out + 1] = X1; cand_c[3 * out + 2] = X2;
+    cand_n[3 * out] = xdiv(q0, dist); cand_n[3 * out + 1] = xdiv(q1, dist); cand_n[3 * out + 2] = xdiv(q2, dist);
+    cand_ref[out] = v;
+    cand_px[2 * out] = (int)u;
+    cand_px[2 * out + 1] = (int)vv;
 }
 
 // accept gate of MVS2.py:369 without the visible_ct clause (applied by the compaction):
@@ -331,7 +346,10 @@ extern "C" int mvs_round_generate(mvs_ctx* ctx, const void* frontier, int64_t F,
         expand_slots<2><<<blocks, 256, 0, s>>>((const uint8_t*)frontier, F, rb, ctx->V, ctx->cell_size, ctx->wc, ctx->hc,
                                               ctx->d_cells, ctx->d_claim, ctx->epoch, ctx->d_counts, ctx->d_geom, ctx->cand_slot,
                                               ctx->cand_parent, ctx->cand_c, ctx->cand_n, ctx->cand_ref, ctx->cand_px);
-        ctx->launches++;
+        expand_geometry<<<(unsigned)((M + 127) / 128), 128, 0, s>>>((const uint8_t*)frontier, rb, ctx->V, ctx->cell_size, M,
+                                                                   ctx->cand_slot, ctx->d_geom, ctx->cand_c, ctx->cand_n,
+                                                                   ctx->cand_ref, ctx->cand_px);
+        ctx->launches += 2;
         MVS_CUDA_CHECK(cudaGetLastError());
     }
     ctx->n_cand = M;
@@ -575,7 +593,10 @@ extern "C" int mvs_expand_run(mvs_ctx* ctx, const void* seeds, int64_t n_seeds, 
                                                                         ctx->d_cells, ctx->d_claim, ctx->epoch, ctx->d_counts,
                                                                         ctx->d_geom, ctx->cand_slot, ctx->cand_parent, ctx->cand_c,
                                                                         ctx->cand_n, ctx->cand_ref, ctx->cand_px);
-            ctx->launches++;
+            expand_geometry<<<(unsigned)((M + 127) / 128), 128, 0, s>>>(frontier, rb, ctx->V, ctx->cell_size, M, ctx->cand_slot,
+                                                                       ctx->d_geom, ctx->cand_c, ctx->cand_n, ctx->cand_ref,
+                                                                       ctx->cand_px);
+            ctx->launches += 2;
             MVS_CUDA_CHECK(cudaGetLastError());
             ctx->n_cand = M;
             // ---- this GPU's shard: score, gate, publish

@@ -647,6 +647,10 @@ int mvs_launch_score_pmvs(mvs_ctx* ctx, int64_t N, const double* c, const double
     static const mvs_ctx* table_owner[64] = {nullptr};
     static int64_t table_serial[64] = {0};
     if (ctx->device < 64 && (table_owner[ctx->device] != ctx || table_serial[ctx->device] != ctx->pmvs_serial)) {
+        // another context's Mode B kernel may still be reading the per-device table on another stream: drain the
+        // device before handing the table over (only when contexts alternate on one GPU; a CUDA graph captured for
+        // one context must not be replayed after another context scored in Mode B -- re-capture it)
+        if (table_owner[ctx->device] != nullptr) MVS_CUDA_CHECK(cudaDeviceSynchronize());
         MVS_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_tex, ctx->pmvs_tex_host, sizeof(cudaTextureObject_t) * ctx->V, 0,
                                                cudaMemcpyHostToDevice, s));
         MVS_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_off, ctx->pmvs_off_host, sizeof(float) * 2 * ctx->V, 0, cudaMemcpyHostToDevice, s));

@@ -160,7 +160,12 @@ __global__ void __launch_bounds__(256)
 }
 
 int mvs_build_window_maps(mvs_ctx* ctx, int wid, cudaStream_t s) {
-    if (ctx->maps_wid == wid && ctx->d_smap && ctx->d_vmap) return MVS_OK;
+    if (ctx->maps_wid == wid && ctx->d_smap && ctx->d_vmap) {
+        // built asynchronously on the first caller's stream: any other stream orders itself behind the build
+        if (ctx->ev_maps && s != ctx->maps_stream) MVS_CUDA_CHECK(cudaStreamWaitEvent(s, ctx->ev_maps, 0));
+        return MVS_OK;
+    }
+    if (ctx->maps_wid >= 0) MVS_CUDA_CHECK(cudaDeviceSynchronize());   // rebuilding for another wid: no reader may be in flight
     const size_t n = (size_t)ctx->H * ctx->W * ctx->Vp;
     int rc;
     if ((rc = mvs_ensure((void**)&ctx->d_smap, &ctx->smap_bytes, n * sizeof(uint16_t) + 256, "window-sum map")) != MVS_OK ||
@@ -185,6 +190,9 @@ int mvs_build_window_maps(mvs_ctx* ctx, int wid, cudaStream_t s) {
 #undef MVS_MAPS
     ctx->launches++;
     MVS_CUDA_CHECK(cudaGetLastError());
+    if (!ctx->ev_maps) MVS_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_maps, cudaEventDisableTiming));
+    MVS_CUDA_CHECK(cudaEventRecord(ctx->ev_maps, s));
+    ctx->maps_stream = s;
     ctx->maps_wid = wid;
     return MVS_OK;
 }
@@ -1062,8 +1070,17 @@ static int launch_gather(mvs_ctx* ctx, const ScoreArgs& A, int64_t N, const uint
         }
         return launch_gather_gs<WID, 16, 0>(ctx, A, N, anchors, entries, s);
     }
-    if (WID == 5 && Q == 32) return launch_gather_gs<WID, 32, 512>(ctx, A, N, anchors, entries, s);
-    if (WID == 5 && Q == 64) return launch_gather_gs<WID, 32, 1024>(ctx, A, N, anchors, entries, s);
+    if (WID == 5 && (Q == 32 || Q == 64)) {
+        const int mb = k1_minb_override();                 // MVS_K1_MINB: resident CTAs per SM (tuning knob)
+        if (Q == 32) {
+            if (mb == 2) return launch_gather_gs<5, 32, 512, 2>(ctx, A, N, anchors, entries, s);
+            if (mb == 3) return launch_gather_gs<5, 32, 512, 3>(ctx, A, N, anchors, entries, s);
+            return launch_gather_gs<5, 32, 512>(ctx, A, N, anchors, entries, s);
+        }
+        if (mb == 2) return launch_gather_gs<5, 32, 1024, 2>(ctx, A, N, anchors, entries, s);
+        if (mb == 3) return launch_gather_gs<5, 32, 1024, 3>(ctx, A, N, anchors, entries, s);
+        return launch_gather_gs<5, 32, 1024>(ctx, A, N, anchors, entries, s);
+    }
     return launch_gather_gs<WID, 32, 0>(ctx, A, N, anchors, entries, s);
 }
 

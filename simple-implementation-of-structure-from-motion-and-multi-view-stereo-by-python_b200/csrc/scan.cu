@@ -82,23 +82,47 @@ __global__ void __launch_bounds__(1024) scan_add_base(int32_t* __restrict__ a, i
     if (i < n) a[i] += (int32_t)tile_tot[blockIdx.x];
 }
 
-// One CTA, one launch: thread t scans the run [t*per, (t+1)*per) serially, the 1024 run totals are scanned
-// block-wide.  For the small arrays of a real expansion round (frontier, candidates, histogram bins),
-// where three dependent launches cost more than the scan itself.
-#define MVS_SCAN_SMALL_MAX (1024 * 160)
-__global__ void __launch_bounds__(1024) scan_small(int32_t* __restrict__ a, int n, int per, int64_t* __restrict__ total) {
+// Up to 4096 elements: one CTA, one launch (thread t owns 4 consecutive elements).
+#define MVS_SCAN_SMALL_MAX 4096
+__global__ void __launch_bounds__(1024) scan_small(int32_t* __restrict__ a, int n, int64_t* __restrict__ total) {
     __shared__ int wsum[32];
-    const int lo = threadIdx.x * per, hi = min(lo + per, n);
-    int sum = 0;
-    for (int i = lo; i < hi; ++i) sum += a[i];
+    const int lo = threadIdx.x * 4;
+    int v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = (lo + k < n) ? a[lo + k] : 0;
+    const int sum = v[0] + v[1] + v[2] + v[3];
     int tot;
     int run = block_scan_incl(sum, wsum, &tot) - sum;
-    for (int i = lo; i < hi; ++i) {
-        const int v = a[i];
-        a[i] = run;
-        run += v;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (lo + k < n) a[lo + k] = run;
+        run += v[k];
     }
     if (threadIdx.x == 0) *total = tot;
+}
+
+// Up to MVS_SCAN_MID_TILES tiles of 1024: two launches -- scan_tiles, then every CTA reduces the totals of the
+// tiles before it itself (a few hundred values) and adds the base; the last CTA writes the grand total.
+#define MVS_SCAN_MID_TILES 2048
+__global__ void __launch_bounds__(1024) scan_add_base_reduce(int32_t* __restrict__ a, int64_t n, const int64_t* __restrict__ tile_tot,
+                                                             int T, int64_t* __restrict__ total) {
+    __shared__ long long wsum[32];
+    __shared__ long long s_base;
+    long long part = 0;
+    for (int i = threadIdx.x; i < (int)blockIdx.x; i += 1024) part += tile_tot[i];
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) part += __shfl_xor_sync(FULL, part, sft);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long b = 0;
+        for (int w = 0; w < 32; ++w) b += wsum[w];
+        s_base = b;
+        if ((int)blockIdx.x == T - 1) *total = b + tile_tot[T - 1];
+    }
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+    if (i < n) a[i] += (int32_t)s_base;
 }
 
 int mvs_exclusive_scan_i32(int32_t* a, int64_t n, int64_t* tile_scratch, int64_t* total, cudaStream_t s) {
@@ -107,7 +131,14 @@ int mvs_exclusive_scan_i32(int32_t* a, int64_t n, int64_t* tile_scratch, int64_t
         return MVS_OK;
     }
     if (n <= MVS_SCAN_SMALL_MAX) {
-        scan_small<<<1, 1024, 0, s>>>(a, (int)n, (int)((n + 1023) / 1024), total);
+        scan_small<<<1, 1024, 0, s>>>(a, (int)n, total);
+        MVS_CUDA_CHECK(cudaGetLastError());
+        return MVS_OK;
+    }
+    if ((n + 1023) / 1024 <= MVS_SCAN_MID_TILES) {
+        const int Tm = (int)((n + 1023) / 1024);
+        scan_tiles<<<Tm, 1024, 0, s>>>(a, n, tile_scratch);
+        scan_add_base_reduce<<<Tm, 1024, 0, s>>>(a, n, tile_scratch, Tm, total);
         MVS_CUDA_CHECK(cudaGetLastError());
         return MVS_OK;
     }

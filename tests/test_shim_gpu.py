@@ -105,10 +105,11 @@ def test_dense_points_end_to_end(golden, built_lib, tmp_path, monkeypatch):
     sel = sel[sel >= 0]
     assert len(sel) == len(init) and np.abs(sc["c"][sel] - seeds_c).max() < 1e-12
     table = np.ones((V, 160, 120), dtype=bool)
-    ci, cj = np.floor(o["xy"][sel, 0] / 2).astype(int), np.floor(o["xy"][sel, 1] / 2).astype(int)
+    oxy = np.stack([o["x"], o["y"]], axis=1)
+    ci, cj = np.floor(oxy[sel, 0] / 2).astype(int), np.floor(oxy[sel, 1] / 2).astype(int)
     for k, i in enumerate(sel):
         table[np.nonzero(o["vis"][i])[0], ci[k], cj[k]] = False                        # fill_with_point, MVS2.py:258-259
-    fr = dict(c=seeds_c.copy(), n=sc["n"][sel], vis=o["vis"][sel], xy=o["xy"][sel])
+    fr = dict(c=seeds_c.copy(), n=sc["n"][sel], vis=o["vis"][sel], xy=oxy[sel])
     off = 0
     for rnd, st in enumerate(stats):
         cand, fr = expansion.expand_round(gray, cams, fr, table, float(e["scale"]), int(e["bound"]))
