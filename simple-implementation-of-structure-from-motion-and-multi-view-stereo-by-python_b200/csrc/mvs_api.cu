@@ -277,7 +277,6 @@ extern "C" int mvs_destroy(mvs_ctx* ctx) {
     for (void* b : more2)
         if (b) cudaFree(b);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
-    if (ctx->ev_maps) cudaEventDestroy(ctx->ev_maps);
     for (int i = 0; i < 2; ++i)
         if (ctx->ev_round[i]) cudaEventDestroy(ctx->ev_round[i]);
     for (int i = 0; i < 2 * MVS_PROF_RING; ++i)

@@ -50,8 +50,6 @@ struct mvs_ctx {
     uint32_t* d_vmap;
     size_t smap_bytes, vmap_bytes;
     int maps_wid;
-    cudaEvent_t ev_maps;  // recorded after the map build; other streams wait on it
-    cudaStream_t maps_stream;
     // spatial binning scratch (bin.cu): hypotheses ordered by 8x8-pixel anchor tile
     int32_t* d_bin_hist;   // [tiles + 2]
     int32_t* d_bin_key;    // [N]

@@ -160,11 +160,7 @@ __global__ void __launch_bounds__(256)
 }
 
 int mvs_build_window_maps(mvs_ctx* ctx, int wid, cudaStream_t s) {
-    if (ctx->maps_wid == wid && ctx->d_smap && ctx->d_vmap) {
-        // built asynchronously on the first caller's stream: any other stream orders itself behind the build
-        if (ctx->ev_maps && s != ctx->maps_stream) MVS_CUDA_CHECK(cudaStreamWaitEvent(s, ctx->ev_maps, 0));
-        return MVS_OK;
-    }
+    if (ctx->maps_wid == wid && ctx->d_smap && ctx->d_vmap) return MVS_OK;
     if (ctx->maps_wid >= 0) MVS_CUDA_CHECK(cudaDeviceSynchronize());   // rebuilding for another wid: no reader may be in flight
     const size_t n = (size_t)ctx->H * ctx->W * ctx->Vp;
     int rc;
@@ -190,9 +186,12 @@ int mvs_build_window_maps(mvs_ctx* ctx, int wid, cudaStream_t s) {
 #undef MVS_MAPS
     ctx->launches++;
     MVS_CUDA_CHECK(cudaGetLastError());
-    if (!ctx->ev_maps) MVS_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_maps, cudaEventDisableTiming));
-    MVS_CUDA_CHECK(cudaEventRecord(ctx->ev_maps, s));
-    ctx->maps_stream = s;
+    // The maps are shared by every later call on ANY stream: the build (once per context and wid, ~0.1 ms) is
+    // waited for here, so that no other stream can ever read half-built maps.  (Not possible while `s` is being
+    // captured into a CUDA graph: build the maps with one eager call before capturing.)
+    cudaStreamCaptureStatus capst = cudaStreamCaptureStatusNone;
+    MVS_CUDA_CHECK(cudaStreamIsCapturing(s, &capst));
+    if (capst == cudaStreamCaptureStatusNone) MVS_CUDA_CHECK(cudaStreamSynchronize(s));
     ctx->maps_wid = wid;
     return MVS_OK;
 }
