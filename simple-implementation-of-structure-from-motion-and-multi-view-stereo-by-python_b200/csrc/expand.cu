@@ -127,7 +127,8 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(128)
     expand_geometry(const uint8_t* __restrict__ frontier, int rec_bytes, int V, int cs, int64_t M,
                     const int64_t* __restrict__ cand_slot, const CamGeom* __restrict__ geom, double* __restrict__ cand_c,
-                    double* __restrict__ cand_n, int32_t* __restrict__ cand_ref, int32_t* __restrict__ cand_px) {
+                    double* __restrict__ cand_n, int32_t* __restrict__ cand_ref, int32_t* __restrict__ cand_px,
+                    uint8_t* __restrict__ gate = nullptr, double dist_limit = 0.0) {
     const int64_t out = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (out >= M) return;
     const long long slot = cand_slot[out];
@@ -160,6 +161,16 @@ __global__ void __launch_bounds__(128)
     cand_ref[out] = v;
     cand_px[2 * out] = (int)u;
     cand_px[2 * out + 1] = (int)vv;
+    if (gate) {
+        // the accept gate of MVS2.py:369 depends on geometry only (same operations as expand_gate)
+        const double n0 = xdiv(q0, dist), n1 = xdiv(q1, dist), n2 = xdiv(q2, dist);
+        const double e0 = xsub(p->c[0], X0), e1 = xsub(p->c[1], X1), e2 = xsub(p->c[2], X2);
+        const double a = dot3(e0, e1, e2, p->n[0], p->n[1], p->n[2]);
+        const double b = dot3(e0, e1, e2, n0, n1, n2);
+        const bool neigh = fabs(xadd(a, b)) < 0.1;
+        const double dd = sqrt(dot3(e0, e1, e2, e0, e1, e2));
+        gate[out] = (neigh && dd < dist_limit) ? 1 : 0;
+    }
 }
 
 // accept gate of MVS2.py:369 without the visible_ct clause (applied by the compaction):
@@ -359,7 +370,7 @@ extern "C" int mvs_round_generate(mvs_ctx* ctx, const void* frontier, int64_t F,
 
 // shared body of mvs_round_score / mvs_round_score_p2p: score the shard and evaluate the gate
 static int round_score_shard(mvs_ctx* ctx, const void* frontier, int64_t begin, int64_t end, double min_ncc, int wid,
-                             double scale, cudaStream_t s) {
+                             double scale, cudaStream_t s, bool gate_done = false) {
     const int64_t n = end - begin;
     if (n == 0) return MVS_OK;
     const size_t mw = (size_t)((ctx->V + 63) / 64);
@@ -367,6 +378,7 @@ static int round_score_shard(mvs_ctx* ctx, const void* frontier, int64_t begin, 
                                        ctx->cand_vis + mw * begin, ctx->cand_avg + begin, ctx->cand_count + begin,
                                        ctx->cand_xy + 2 * begin, nullptr, s);
     if (rc != MVS_OK) return rc;
+    if (gate_done) return MVS_OK;                              // mvs_expand_run: expand_geometry already wrote the gate
     expand_gate<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((const uint8_t*)frontier, rec_bytes_of(ctx), begin, end,
                                                            ctx->cand_parent, ctx->cand_c, ctx->cand_n, 0.05 / scale,
                                                            ctx->cand_gate);
@@ -595,13 +607,13 @@ extern "C" int mvs_expand_run(mvs_ctx* ctx, const void* seeds, int64_t n_seeds, 
                                                                         ctx->cand_n, ctx->cand_ref, ctx->cand_px);
             expand_geometry<<<(unsigned)((M + 127) / 128), 128, 0, s>>>(frontier, rb, ctx->V, ctx->cell_size, M, ctx->cand_slot,
                                                                        ctx->d_geom, ctx->cand_c, ctx->cand_n, ctx->cand_ref,
-                                                                       ctx->cand_px);
+                                                                       ctx->cand_px, ctx->cand_gate, 0.05 / prm->scale);
             ctx->launches += 2;
             MVS_CUDA_CHECK(cudaGetLastError());
             ctx->n_cand = M;
             // ---- this GPU's shard: score, gate, publish
             const int64_t begin = (M * rank) / world, end = (M * (rank + 1)) / world;
-            if ((rc = round_score_shard(ctx, frontier, begin, end, prm->min_ncc, prm->wid, prm->scale, s)) != MVS_OK) return rc;
+            if ((rc = round_score_shard(ctx, frontier, begin, end, prm->min_ncc, prm->wid, prm->scale, s, true)) != MVS_OK) return rc;
             void* local_tab[1];
             void* const* inbox_tab = prm->peer_inbox;
             const void* inbox_local;

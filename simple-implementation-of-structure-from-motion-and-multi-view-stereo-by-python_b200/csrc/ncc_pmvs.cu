@@ -8,19 +8,20 @@
 // every view, image-aligned integer lattice, no interpolation, the bounds rule of
 // HarrisFeatures.py:128) and must then agree with K1.
 //
-// Hardware mapping: one warp per hypothesis (per hypothesis SET when selecting), lanes span
-// the mu*mu samples (ceil(mu^2/32) per lane).
-//   * per 16 views, lane v prepares view v: the projection of the patch centre through
-//     K_v (R'_v c + t_v) in fp64 and the per-step increments RELATIVE to it in fp32, staged in
-//     shared memory; a tap position is then 6 FMA + 1 reciprocal, accurate to ~1e-6 px;
-//   * the four bilinear taps of a sample come from ONE texture-gather instruction (tld4) on
-//     a per-view 2-D texture of the gray image (the texture path, not the LSU), as
-//     normalised floats; interpolation weights are exact fp32, not the sampler's 8-bit ones;
-//   * NCC sums are taken on pivot-shifted samples (x - x[lane 0]) so that low-variance
-//     windows keep full fp32 precision, and reduced across the warp with a transposing
-//     butterfly: 16 shuffles per quantity per 16 views instead of 5 per view;
-//   * the best hypothesis of a set (highest mean NCC among those with >= bound visible views,
-//     lowest index on ties) is tracked in registers and written once per set.
+// Hardware mapping (DESIGN.md section "K2"): ONE WARP PER CTA, one hypothesis (or one hypothesis SET when
+// selecting) per warp iteration.
+//   * staging: per 32 views, lane v prepares view v -- the projection of the patch centre through
+//     K_v (R'_v c + t_v) in fp64 and the per-step increments RELATIVE to it in fp32 -- into shared memory; a tap
+//     position is then 6 FMA + 1 reciprocal, accurate to ~1e-6 px;
+//   * phase 1, lanes span the mu*mu samples (ceil(mu^2/32) per lane): the four bilinear taps of a sample come
+//     from ONE texture-gather instruction (tld4) on a gather-enabled 2-D ATLAS that holds every view as a tile
+//     (the texture path, not the LSU), as normalised floats; interpolation weights are exact fp32, not the
+//     sampler's 8-bit ones; the interpolated values of 16 views go to shared memory [view][sample]; a half whose
+//     16 views are all "safe" (footprint provably inside the image) runs without per-tap bounds tests;
+//   * phase 2, lanes span the VIEWS: lane L sums half of the samples of view L & 15 on pivot-shifted values
+//     (x - x[0], so low-variance windows keep full fp32 precision); one shuffle per quantity joins the halves;
+//   * the best hypothesis of a set (highest mean NCC among those with >= bound visible views, lowest index on
+//     ties) is tracked in registers and written once per set.
 // Tensor cores are not used: a gather-bound reduction has no dense contraction.
 #include "project.cuh"
 #include "scan.cuh"
@@ -65,46 +66,6 @@ struct PmvsArgs {
     int32_t* best_idx;
     double* best_avg;
 };
-
-// view-in-group index held by a lane after the transposing butterfly below
-__device__ __forceinline__ int lane_view16(int lane) {
-    return ((lane >> 4) & 1) + 8 * ((lane >> 3) & 1) + 4 * ((lane >> 2) & 1) + 2 * ((lane >> 1) & 1);
-}
-
-// Reduce 16 per-view partials across the warp: on return every lane holds the complete sum
-// of view lane_view16(lane).  16 shuffles.
-__device__ __forceinline__ float butterfly16f(const float (&a)[16], int lane) {
-    float b[8];
-    const bool h16 = lane & 16;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        const float keep = h16 ? a[2 * q + 1] : a[2 * q];
-        const float send = h16 ? a[2 * q] : a[2 * q + 1];
-        b[q] = keep + __shfl_xor_sync(FULL, send, 16);
-    }
-    float c4[4];
-    const bool h8 = lane & 8;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const float keep = h8 ? b[q + 4] : b[q];
-        const float send = h8 ? b[q] : b[q + 4];
-        c4[q] = keep + __shfl_xor_sync(FULL, send, 8);
-    }
-    float d2[2];
-    const bool h4 = lane & 4;
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-        const float keep = h4 ? c4[q + 2] : c4[q];
-        const float send = h4 ? c4[q] : c4[q + 2];
-        d2[q] = keep + __shfl_xor_sync(FULL, send, 4);
-    }
-    const bool h2 = lane & 2;
-    const float keep = h2 ? d2[1] : d2[0];
-    const float send = h2 ? d2[0] : d2[1];
-    float e = keep + __shfl_xor_sync(FULL, send, 2);
-    e += __shfl_xor_sync(FULL, e, 1);
-    return e;
-}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
