@@ -465,46 +465,48 @@ __global__ void __launch_bounds__(256, MINB)
     const uint32_t hmask = hyp_mask<LPH>(sub);
     uint32_t(*sref)[K][NG] = s_ref[wib][sub];
 
-    // every lane group walks its own run of 2*ITERS consecutive positions and pairs a position with its
-    // successor whenever both read the same quads (a fixed even/odd pairing lost 40 % of the pairs on the
-    // sparse 1080p / 4K rings: a bin that starts at an odd position was split)
-    constexpr int RUN = 2 * ITERS;
     for (int64_t i0 = (int64_t)blockIdx.x * CHUNK; i0 < N; i0 += (int64_t)gridDim.x * CHUNK) {
-        int64_t pos = i0 + (int64_t)((wib * HPW + sub) * RUN);
-        const int64_t end = (pos + RUN < N) ? pos + RUN : N;
-        while (pos < end) {
-            const int64_t i = pos;
+        for (int it = 0; it < ITERS; ++it) {
+            const int64_t i = i0 + 2 * ((it * 8 + wib) * HPW + sub);
+            if (i >= N) continue;                          // the whole lane group leaves together
             uint32_t a0, a1 = MVS_ANCHOR_INVALID;
             int64_t h0 = i, h1 = i + 1;
             if (entries) {                                 // ordered batch: (hypothesis index, anchor) pairs
                 const uint2 e0 = __ldg(entries + i);
                 h0 = e0.x;
                 a0 = e0.y;
-                if (i + 1 < end) {
+                if (i + 1 < N) {
                     const uint2 e1 = __ldg(entries + i + 1);
                     h1 = e1.x;
                     a1 = e1.y;
                 }
             } else {
                 a0 = __ldg(anchors + i);
-                if (i + 1 < end) a1 = __ldg(anchors + i + 1);
+                if (i + 1 < N) a1 = __ldg(anchors + i + 1);
             }
             const bool ok0 = a0 != MVS_ANCHOR_INVALID, ok1 = a1 != MVS_ANCHOR_INVALID;
             const bool same = ok0 && ok1 && ((a0 >> 16) == (a1 >> 16)) &&
                               ((((int)(a0 & 0xffffu) - WID) >> 2) == (((int)(a1 & 0xffffu) - WID) >> 2));
-            pos += same ? 2 : 1;
             if (same) {
                 const uint32_t aa[2] = {a0, a1};
                 const int64_t hh[2] = {h0, h1};
                 score_block<WID, LPH, 2, GS, WANT_NCC>(A, aa, hh, sref, lih, hmask);
-            } else if (ok0) {
-                const uint32_t aa[1] = {a0};
-                const int64_t hh[1] = {h0};
-                score_block<WID, LPH, 1, GS, WANT_NCC>(A, aa, hh, sref, lih, hmask);
+            } else {
+                const uint32_t a2[2] = {a0, a1};
+                const int64_t h2[2] = {h0, h1};
+#pragma unroll 1
+                for (int t = 0; t < 2; ++t) {              // one code instance for both singles
+                    if (a2[t] == MVS_ANCHOR_INVALID) continue;
+                    const uint32_t aa[1] = {a2[t]};
+                    const int64_t hh[1] = {h2[t]};
+                    score_block<WID, LPH, 1, GS, WANT_NCC>(A, aa, hh, sref, lih, hmask);
+                }
             }
         }
     }
 }
+
+
 
 // ---------------------------------------------------------------------------------
 // K1 for 33..48 views (dinoRing's 48, the temple-shaped 47): "quad + pair" lanes.
@@ -533,12 +535,12 @@ __device__ __forceinline__ uint32_t seg8_or(uint32_t v) {
 
 template <int WID, int GS, int MINB, bool WANT_NCC>
 __global__ void __launch_bounds__(256, MINB)
-    ncc_score_gather6(const ScoreArgs A, int64_t N, const uint32_t* __restrict__ anchors, const uint2* __restrict__ entries) {
+    ncc_score_gather6(const ScoreArgs A, int64_t N, const uint32_t* __restrict__ anchors, const uint2* __restrict__ entries,
+                      int PER) {
     constexpr int K = 2 * WID + 1;
     constexpr int NG = (K + 6) / 4;
     constexpr int NPIX = K * K;
-    constexpr int PER = MVS_K6_PER;
-    constexpr int CHUNK = 32 * PER;                        // 8 warps x 4 lane groups x PER positions
+    const int CHUNK = 32 * PER;                            // 8 warps x 4 lane groups x PER positions
     __shared__ __align__(16) uint32_t s_ref[8][4][2][K][NG];
 
     const int lane = threadIdx.x & 31;
@@ -839,39 +841,43 @@ __global__ void __launch_bounds__(256, MINB)
     const int sub = lane / LPH;
     const int lih = lane % LPH;
     uint32_t acc = 0u;
-    constexpr int RUN = 2 * ITERS;
     for (int64_t i0 = (int64_t)blockIdx.x * CHUNK; i0 < N; i0 += (int64_t)gridDim.x * CHUNK) {
-        int64_t pos = i0 + (int64_t)((wib * HPW + sub) * RUN);
-        const int64_t end = (pos + RUN < N) ? pos + RUN : N;
-        while (pos < end) {
-            const int64_t i = pos;
+        for (int it = 0; it < ITERS; ++it) {
+            const int64_t i = i0 + 2 * ((it * 8 + wib) * HPW + sub);
+            if (i >= N) continue;
             uint32_t a0, a1 = MVS_ANCHOR_INVALID;
             int64_t h0 = i, h1 = i + 1;
             if (entries) {
                 const uint2 e0 = __ldg(entries + i);
                 h0 = e0.x;
                 a0 = e0.y;
-                if (i + 1 < end) {
+                if (i + 1 < N) {
                     const uint2 e1 = __ldg(entries + i + 1);
                     h1 = e1.x;
                     a1 = e1.y;
                 }
             } else {
                 a0 = __ldg(anchors + i);
-                if (i + 1 < end) a1 = __ldg(anchors + i + 1);
+                if (i + 1 < N) a1 = __ldg(anchors + i + 1);
             }
             const bool ok0 = a0 != MVS_ANCHOR_INVALID, ok1 = a1 != MVS_ANCHOR_INVALID;
             const bool same = ok0 && ok1 && ((a0 >> 16) == (a1 >> 16)) &&
                               ((((int)(a0 & 0xffffu) - WID) >> 2) == (((int)(a1 & 0xffffu) - WID) >> 2));
-            pos += same ? 2 : 1;
             if (same) {
                 const uint32_t aa[2] = {a0, a1};
                 const int64_t hh[2] = {h0, h1};
                 acc ^= probe_block<WID, LPH, 2, GS>(A, aa, hh, lih);
-            } else if (ok0) {
-                const uint32_t aa[1] = {a0};
-                const int64_t hh[1] = {h0};
-                acc ^= probe_block<WID, LPH, 1, GS>(A, aa, hh, lih);
+            } else {
+                if (ok0) {
+                    const uint32_t aa[1] = {a0};
+                    const int64_t hh[1] = {h0};
+                    acc ^= probe_block<WID, LPH, 1, GS>(A, aa, hh, lih);
+                }
+                if (ok1) {
+                    const uint32_t aa[1] = {a1};
+                    const int64_t hh[1] = {h1};
+                    acc ^= probe_block<WID, LPH, 1, GS>(A, aa, hh, lih);
+                }
             }
         }
     }
@@ -883,11 +889,10 @@ __global__ void __launch_bounds__(256, MINB)
 template <int WID, int GS, int MINB>
 __global__ void __launch_bounds__(256, MINB)
     gather_probe6(const ScoreArgs A, int64_t N, const uint32_t* __restrict__ anchors, const uint2* __restrict__ entries,
-                  uint32_t* __restrict__ sink) {
+                  uint32_t* __restrict__ sink, int PER) {
     constexpr int K = 2 * WID + 1;
     constexpr int NG = (K + 6) / 4;
-    constexpr int PER = MVS_K6_PER;
-    constexpr int CHUNK = 32 * PER;
+    const int CHUNK = 32 * PER;
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     const int grp = lane >> 3;
@@ -979,16 +984,22 @@ __global__ void __launch_bounds__(256, MINB)
 template <int WID, int GS, int MINB = MVS_K6_MINB>
 static int launch_gather6(mvs_ctx* ctx, const ScoreArgs& A, int64_t N, const uint32_t* anchors, const uint2* entries,
                           cudaStream_t s) {
-    const int64_t chunk = 32 * MVS_K6_PER;
+    static int per = 0;                                    // MVS_K6_PER: positions per lane-group run (tuning knob)
+    if (per == 0) {
+        const char* e = getenv("MVS_K6_PER");
+        per = e ? atoi(e) : MVS_K6_PER;
+        if (per < 2 || per > 1024) per = MVS_K6_PER;
+    }
+    const int64_t chunk = 32 * (int64_t)per;
     const int64_t want = (N + chunk - 1) / chunk;
     const int64_t cap = (int64_t)ctx->sm_count * MINB * 8;
     const int blocks = (int)(want < cap ? want : cap);
     if (ctx->probe_gather)
-        gather_probe6<WID, GS, MINB><<<blocks, 256, 0, s>>>(A, N, anchors, entries, (uint32_t*)ctx->d_bin_hist);
+        gather_probe6<WID, GS, MINB><<<blocks, 256, 0, s>>>(A, N, anchors, entries, (uint32_t*)ctx->d_bin_hist, per);
     else if (A.ncc_out)
-        ncc_score_gather6<WID, GS, MINB, true><<<blocks, 256, 0, s>>>(A, N, anchors, entries);
+        ncc_score_gather6<WID, GS, MINB, true><<<blocks, 256, 0, s>>>(A, N, anchors, entries, per);
     else
-        ncc_score_gather6<WID, GS, MINB, false><<<blocks, 256, 0, s>>>(A, N, anchors, entries);
+        ncc_score_gather6<WID, GS, MINB, false><<<blocks, 256, 0, s>>>(A, N, anchors, entries, per);
     return MVS_OK;
 }
 
