@@ -441,22 +441,14 @@ def patch_expansion(args, imgs, initial_patches, cells, camera_pos, visible_lowe
     seeds = be.to_device(_patches_to_records(initial_patches, V))
     mode = os.environ.get("MVS_ROUNDS", "fused")
     if mode == "fused" and world > 1:
-        # the fused exchange needs NCCL-style symmetric memory with peer access on ONE box: agree on it
-        # collectively, otherwise every rank falls back to the stepwise driver with a collective all-gather
-        import torch
-        ok = 1
-        try:
-            if dist.get_backend() != "nccl":
-                raise RuntimeError("backend is not nccl")
-            be.exchange_setup(int(os.environ.get("MVS_ROUND_CAPACITY", str(1 << 21))), world, dist.group.WORLD)
-        except Exception as e:                                # noqa: any failure -> collective fallback
-            ok = 0
-            why = repr(e)
-        flag = torch.tensor([ok], dtype=torch.int32, device=be.device if dist.get_backend() == "nccl" else "cpu")
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        if int(flag.item()) == 0:
+        # the fused exchange needs NCCL symmetric memory with peer access on ONE box: agree on it collectively,
+        # otherwise every rank falls back to the stepwise driver with a collective all-gather
+        from .rounds import agree_on_fused_exchange
+        cap = int(os.environ.get("MVS_ROUND_CAPACITY", str(1 << 21)))
+        ok, why = agree_on_fused_exchange(lambda: be.exchange_setup(cap, world, dist.group.WORLD), dist, be.device)
+        if not ok:
             if rank == 0:
-                print("patch_expansion: fused P2P exchange unavailable (%s); using the collective all-gather" % (why if not ok else "on a peer"))
+                print("patch_expansion: fused P2P exchange unavailable (%s); using the collective all-gather" % why)
             mode = "stepwise"
     if mode == "fused":
         stats, n_new = be.expand_run(seeds, max_rounds=max_rounds, max_iterations=max_iter, max_patches=max_patches,

@@ -523,7 +523,7 @@ __global__ void __launch_bounds__(256, MINB)
 // partial-mask collectives) and stay inside their 8-lane segment.
 // ---------------------------------------------------------------------------------
 #ifndef MVS_K6_PER
-#define MVS_K6_PER 16
+#define MVS_K6_PER 8            // positions per lane-group run: measured 0.331 ms (8) / 0.343 (4) / 0.358 (16) / 0.363 (32) / 0.437 (64) per 2^20 hypotheses
 #endif
 
 __device__ __forceinline__ uint32_t seg8_or(uint32_t v) {

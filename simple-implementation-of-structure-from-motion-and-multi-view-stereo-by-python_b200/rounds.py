@@ -214,6 +214,27 @@ class DeviceBackend:
         return nxt[: int(self._n.item())]
 
 
+def agree_on_fused_exchange(setup, dist, device=None, require_nccl=True):
+    """Collective decision whether every rank can run the fused multi-GPU pipeline (mvs_expand_run with the
+    minimal wire over peer-mapped symmetric memory).  ``setup()`` performs this rank's part (allocation +
+    rendezvous) and may raise; the fused path needs an NCCL process group on ONE box with peer access.  All
+    ranks return the same answer: True only if every rank succeeded -- otherwise every rank falls back to the
+    stepwise driver with a torch.distributed all-gather.  Returns (ok, reason).  ``require_nccl=False`` lets the
+    CPU tests exercise the decision over gloo."""
+    import torch
+    ok, why = 1, ""
+    try:
+        if require_nccl and dist.get_backend() != "nccl":
+            raise RuntimeError("process group backend is %r, not nccl" % dist.get_backend())
+        setup()
+    except Exception as e:                                    # noqa: any failure -> collective fallback
+        ok, why = 0, repr(e)
+    flag = torch.tensor([ok], dtype=torch.int32, device=device if (device is not None and dist.get_backend() == "nccl") else "cpu")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    agreed = bool(int(flag.item()))
+    return agreed, (why if not ok else ("" if agreed else "a peer rank could not set the exchange up"))
+
+
 def shard_bounds(M, rank, world):
     """Block partition of the candidate list by global candidate index."""
     return (M * rank) // world, (M * (rank + 1)) // world

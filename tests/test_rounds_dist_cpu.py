@@ -129,3 +129,42 @@ def test_shard_bounds_cover_everything():
             assert b[0][0] == 0 and b[-1][1] == M
             assert all(b[i][1] == b[i + 1][0] for i in range(world - 1))
             assert max(e - s for s, e in b) - min(e - s for s, e in b) <= 1
+
+
+def _agree(rank, world, port, fail_rank, q):
+    from mvs_b200.rounds import agree_on_fused_exchange
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    calls = []
+
+    def setup():
+        calls.append(1)
+        if rank == fail_rank:
+            raise RuntimeError("no peer access")
+    # 1) gloo is not an NCCL group: every rank declines WITHOUT attempting the set-up
+    ok1, _ = agree_on_fused_exchange(setup, dist)
+    n1 = len(calls)
+    # 2) the all-or-nothing decision itself (transport requirement lifted)
+    ok2, why2 = agree_on_fused_exchange(setup, dist, require_nccl=False)
+    q.put((rank, ok1, n1, ok2, why2))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("fail_rank", [-1, 1])
+def test_fused_exchange_is_an_all_or_nothing_decision(fail_rank):
+    """patch_expansion's choice between the fused P2P pipeline and the collective fallback must be the same
+    on every rank (a rank that went its own way would dead-lock the others in the first device barrier)."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_agree, args=(r, world, port, fail_rank, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = sorted([q.get(timeout=300) for _ in procs], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(o[1] is False and o[2] == 0 for o in out)              # gloo: declined, set-up never attempted
+    assert len(set(o[3] for o in out)) == 1                           # same answer everywhere
+    assert out[0][3] == (fail_rank < 0)
