@@ -98,6 +98,26 @@ def test_other_window_sizes_against_oracle(golden, built_lib, wid):
                               equal_nan=True), k
 
 
+@pytest.mark.parametrize("V,wid,N", [(100, 2, 5000), (100, 7, 9000), (66, 3, 9000), (129, 4, 9000)])
+def test_large_ring_other_windows(built_lib, V, wid, N):
+    """65+ views (the 32-lane kernel, passes of 128 views) at window sizes other than the reference's, with view
+    counts that are not multiples of 32."""
+    import mvs_b200
+    from mvs_b200 import rings
+    from oracle import mode_a
+    rgb, K, R, t = rings.make_ring(V, 96, 128, seed=21)
+    c, n, ref = rings.surface_hypotheses(N, K, R, t, seed=22)
+    cams = _oracle_cams(K, R, t)
+    with mvs_b200.MvsContext(rgb, K, R, t, Rrt=cams.R) as ctx:
+        out = ctx.score_host(c, ref, min_ncc=0.7, wid=wid, want_ncc=True)
+        plain = ctx.score_host(c, ref, min_ncc=0.7, wid=wid)               # the variant without the per-view dump
+    o = mode_a.score(mode_a.gray_from_rgb(rgb), cams, c, ref, 0.7, wid=wid)
+    _compare(out, o["vis"], o["ncc"], o["avg"], V)
+    for k in ("vis_mask", "count", "avg"):
+        assert np.array_equal(plain[k], out[k]), k
+    assert o["valid"].mean() > 0.3 and o["count"].max() >= 3
+
+
 @pytest.mark.parametrize("V,H,W,N", [(48, 480, 640, 6000), (70, 120, 200, 6000), (33, 97, 131, 6000), (130, 120, 160, 6000),
                                      (7, 120, 160, 6000), (260, 120, 160, 6000),
                                      # >= 8192 hypotheses: the tile-ordered path with shared loads for neighbours
