@@ -67,6 +67,14 @@ struct PmvsArgs {
     double* best_avg;
 };
 
+// 1/x as ONE MUFU.RCP (__fdividef(1, x) compiles to five instructions: a denormal-range test, a scaling and a
+// rescaling around the same MUFU.RCP; the denominators here are depths of ~0.5, never denormal)
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(FULL, v, s);
@@ -78,11 +86,13 @@ __device__ __forceinline__ float warp_sum(float v) {
 // (uc, vc) of the patch centre, which the staging lane knows in fp64:
 //   u = uc + (a*gxu + b*gyu) / z,  gxu = hx.X - uc*hx.Z, ...,  z = Z0 + a*hxZ + b*hyZ
 // so fp32 only ever carries offsets of a few pixels (error ~1e-6 px instead of ~5e-5 px).
-// uc, vc are split into integer part and fraction.
+// uc, vc are split into integer part and fraction.  Everything is stored divided by Z0 (z/Z0 = 1 + a*ex + b*ey),
+// which leaves TEN floats: every lane fetches them per view as two LDS.128 and one LDS.64 -- the shared-memory
+// wavefronts of these broadcasts are what binds the kernel (ncu: l1tex data pipe 84-89 %).
 struct __align__(16) ViewAffine {
     float iu, fu, iv, fv;
-    float Z0, hxZ, hyZ, gxu;
-    float gyu, gxv, gyv, pad;
+    float ex, ey, gxu, gyu;      // ex = hxZ/Z0, ey = hyZ/Z0 (NaN when the centre is not in front of the view)
+    float gxv, gyv, pad0, pad1;
 };
 
 // Bilinear sample through the gather path.  (u0, v0) = integer tap origin (pixel centres at
@@ -102,7 +112,7 @@ __device__ __forceinline__ float tap4(const bool checked, cudaTextureObject_t te
     return fmaf(fv, bot - top, top);
 }
 
-template <int MU, bool REDUCE_A, int MINB>
+template <int MU, bool REDUCE_A, int MINB, bool ONE_ATLAS>
 __global__ void __launch_bounds__(32, MINB) ncc_score_pmvs(const PmvsArgs A, int64_t N) {
     constexpr int NS = MU * MU;
     constexpr int SPL = (NS + 31) / 32;                    // samples per lane
@@ -118,6 +128,9 @@ __global__ void __launch_bounds__(32, MINB) ncc_score_pmvs(const PmvsArgs A, int
     __shared__ float s_val[16][VSTRIDE];
     __shared__ float s_dref[MU * MU];                      // pivot-shifted samples of the reference view
 
+    // ONE_ATLAS (every BASELINE shape up to 128 x 1080p): all views are tiles of one texture, so its handle is read
+    // from the constant bank ONCE instead of once per view (LDCU + index clamp + R2UR per gather batch entry)
+    const cudaTextureObject_t tex0 = c_tex[0];
     const int lane = threadIdx.x;
     constexpr int wib = 0;
     const int64_t warp0 = blockIdx.x;
@@ -202,7 +215,8 @@ __global__ void __launch_bounds__(32, MINB) ncc_score_pmvs(const PmvsArgs A, int
                 const float2 org = A.off[v];
                 va.iu = (float)ucf + org.x + 1.0f; va.fu = (float)(uc - ucf);
                 va.iv = (float)vcf + org.y + 1.0f; va.fv = (float)(vc - vcf);
-                va.Z0 = (float)Zv;
+                const float Z0 = (float)Zv;
+                const float iZ0 = Z0 > 0.0f ? rcp_approx(Z0) : nanf("");   // behind the camera: every tap test fails on NaN
                 const float rx0 = cf.r[0] * ex[0] + cf.r[1] * ex[1] + cf.r[2] * ex[2];
                 const float rx1 = cf.r[3] * ex[0] + cf.r[4] * ex[1] + cf.r[5] * ex[2];
                 const float rx2 = cf.r[6] * ex[0] + cf.r[7] * ex[1] + cf.r[8] * ex[2];
@@ -211,21 +225,21 @@ __global__ void __launch_bounds__(32, MINB) ncc_score_pmvs(const PmvsArgs A, int
                 const float ry2 = cf.r[6] * ey[0] + cf.r[7] * ey[1] + cf.r[8] * ey[2];
                 // hx.X - uc*hx.Z = step*(fx*rx0 + (cx - uc)*rx2): the principal point cancels against uc
                 const float du = (float)(cv.cx - uc), dv = (float)(cv.cy - vc);
-                va.hxZ = step * rx2;
-                va.hyZ = step * ry2;
-                va.gxu = step * fmaf(du, rx2, cf.fx * rx0);
-                va.gyu = step * fmaf(du, ry2, cf.fx * ry0);
-                va.gxv = step * fmaf(dv, rx2, cf.fy * rx1);
-                va.gyv = step * fmaf(dv, ry2, cf.fy * ry1);
-                va.pad = 0.0f;
+                const float hxZ = step * rx2, hyZ = step * ry2;
+                const float gxu = step * fmaf(du, rx2, cf.fx * rx0), gyu = step * fmaf(du, ry2, cf.fx * ry0);
+                const float gxv = step * fmaf(dv, rx2, cf.fy * rx1), gyv = step * fmaf(dv, ry2, cf.fy * ry1);
+                va.ex = hxZ * iZ0; va.ey = hyZ * iZ0;
+                va.gxu = gxu * iZ0; va.gyu = gyu * iZ0;
+                va.gxv = gxv * iZ0; va.gyv = gyv * iZ0;
+                va.pad0 = va.pad1 = 0.0f;
                 s_view[wib][slot] = va;
                 // "safe" view: the whole mu x mu footprint provably stays inside the image and in front of
                 // the camera (bound on the tap offsets from the staged increments, 0.01 px of slack), so its
                 // taps need no per-tap bounds test
-                const float zmin = va.Z0 - HALF * (fabsf(va.hxZ) + fabsf(va.hyZ));
-                const float izm = __fdividef(1.0f, zmin);     // (an IEEE division's slow path would break the warp-uniformity proof below)
-                const float ru = HALF * (fabsf(va.gxu) + fabsf(va.gyu)) * izm + 0.01f;
-                const float rv = HALF * (fabsf(va.gxv) + fabsf(va.gyv)) * izm + 0.01f;
+                const float zmin = Z0 - HALF * (fabsf(hxZ) + fabsf(hyZ));
+                const float izm = rcp_approx(zmin);            // (an IEEE division's slow path would break the warp-uniformity proof below)
+                const float ru = HALF * (fabsf(gxu) + fabsf(gyu)) * izm + 0.01f;
+                const float rv = HALF * (fabsf(gxv) + fabsf(gyv)) * izm + 0.01f;
                 const float ucl = (float)uc, vcl = (float)vc;
                 return !reduce_a && (zmin > 0.0f) && (ucl - ru >= 0.0f) && (ucl + ru <= wm2 + 0.98f) && (vcl - rv >= 0.0f) &&
                        (vcl + rv <= hm2 + 0.98f);
@@ -235,7 +249,8 @@ __global__ void __launch_bounds__(32, MINB) ncc_score_pmvs(const PmvsArgs A, int
             // so the gathers of a whole batch of views are in flight together).
             auto issue_view = [&](const bool checked, int slot, cudaTextureObject_t tex, float2 off, float (&val)[SPL], bool& ok_all) {
                 const float4* pv = reinterpret_cast<const float4*>(&s_view[wib][slot]);
-                const float4 q0 = pv[0], q1 = pv[1], q2 = pv[2];          // iu fu iv fv | Z0 hxZ hyZ gxu | gyu gxv gyv -
+                const float4 q0 = pv[0], q1 = pv[1];                      // iu fu iv fv | ex ey gxu gyu
+                const float2 q2 = *reinterpret_cast<const float2*>(pv + 2);  // gxv gyv
                 ok_all = true;
 #pragma unroll
                 for (int q = 0; q < SPL; ++q) {
@@ -246,10 +261,12 @@ __global__ void __launch_bounds__(32, MINB) ncc_score_pmvs(const PmvsArgs A, int
                         v0 = (float)row + ak[q] + off.y + 1.0f;
                         fu = fv = 0.0f;
                     } else {
-                        const float z = fmaf(ak[q], q1.z, fmaf(aj[q], q1.y, q1.x));
-                        const float iz = __fdividef(1.0f, z);
-                        const float tu = fmaf(fmaf(ak[q], q2.x, aj[q] * q1.w), iz, q0.y);
-                        const float tv = fmaf(fmaf(ak[q], q2.z, aj[q] * q2.y), iz, q0.w);
+                        const float z = fmaf(ak[q], q1.y, fmaf(aj[q], q1.x, 1.0f));   // depth relative to the centre's
+                        const float iz = rcp_approx(z);
+                        const float tu = fmaf(fmaf(ak[q], q1.w, aj[q] * q1.z), iz, q0.y);
+                        const float tv = fmaf(fmaf(ak[q], q2.y, aj[q] * q2.x), iz, q0.w);
+                        // (floor on the FMA pipe through the 1.5 * 2^23 trick instead of FRND was measured: 4.71 vs 4.73 ms at
+                        // mu = 5, 6.51 vs 6.22 ms at mu = 7 -- not kept)
                         const float flu = floorf(tu), flv = floorf(tv);
                         u0 = q0.x + flu;
                         v0 = q0.z + flv;
@@ -317,7 +334,8 @@ __global__ void __launch_bounds__(32, MINB) ncc_score_pmvs(const PmvsArgs A, int
 #pragma unroll
                             for (int jj = 0; jj < TB; ++jj)
                                 // views past the last one re-sample it (branch-free); their sums are never scored
-                                issue_view(false, half * 16 + j0 + jj, c_tex[min(vbase + j0 + jj, A.V - 1)], c_off[min(vbase + j0 + jj, A.V - 1)], val[jj], okl[jj]);
+                                issue_view(false, half * 16 + j0 + jj, ONE_ATLAS ? tex0 : c_tex[min(vbase + j0 + jj, A.V - 1)],
+                                           make_float2(0.0f, 0.0f), val[jj], okl[jj]);      // the tile origin only enters the bounds tests
 #pragma unroll
                             for (int jj = 0; jj < TB; ++jj) {
                                 if (!okl[jj]) bad |= 1u << (j0 + jj);
@@ -334,7 +352,8 @@ __global__ void __launch_bounds__(32, MINB) ncc_score_pmvs(const PmvsArgs A, int
 #pragma unroll
                             for (int jj = 0; jj < TB; ++jj)
                                 // views past the last one re-sample it (branch-free); their sums are never scored
-                                issue_view(true, half * 16 + j0 + jj, c_tex[min(vbase + j0 + jj, A.V - 1)], c_off[min(vbase + j0 + jj, A.V - 1)], val[jj], okl[jj]);
+                                issue_view(true, half * 16 + j0 + jj, ONE_ATLAS ? tex0 : c_tex[min(vbase + j0 + jj, A.V - 1)],
+                                           c_off[min(vbase + j0 + jj, A.V - 1)], val[jj], okl[jj]);
 #pragma unroll
                             for (int jj = 0; jj < TB; ++jj) {
                                 if (!okl[jj]) bad |= 1u << (j0 + jj);
@@ -640,16 +659,19 @@ int mvs_launch_score_pmvs(mvs_ctx* ctx, int64_t N, const double* c, const double
         const char* e = getenv("MVS_K2_MINB");
         minb = e ? atoi(e) : 32;                           // 32 one-warp CTAs per SM (64 registers) measured best
     }
-#define PMVS_LAUNCH(MU_)                                                         \
-    case MU_:                                                                    \
-        if (flags & MVS_PMVS_REDUCE_TO_REFEXACT)                                 \
-            ncc_score_pmvs<MU_, true, 16><<<(int)blocks, 32, 0, s>>>(A, N);      \
-        else if (minb == 16)                                                     \
-            ncc_score_pmvs<MU_, false, 16><<<(int)blocks, 32, 0, s>>>(A, N);     \
-        else if (minb == 24)                                                     \
-            ncc_score_pmvs<MU_, false, 24><<<(int)blocks, 32, 0, s>>>(A, N);     \
-        else                                                                     \
-            ncc_score_pmvs<MU_, false, 32><<<(int)blocks, 32, 0, s>>>(A, N);     \
+    const bool one = ctx->pmvs_n_atlas == 1;
+#define PMVS_LAUNCH(MU_)                                                                                   \
+    case MU_:                                                                                              \
+        if (flags & MVS_PMVS_REDUCE_TO_REFEXACT)                                                           \
+            ncc_score_pmvs<MU_, true, 16, false><<<(int)blocks, 32, 0, s>>>(A, N);                         \
+        else if (minb == 16)                                                                               \
+            ncc_score_pmvs<MU_, false, 16, false><<<(int)blocks, 32, 0, s>>>(A, N);                        \
+        else if (minb == 24)                                                                               \
+            ncc_score_pmvs<MU_, false, 24, false><<<(int)blocks, 32, 0, s>>>(A, N);                        \
+        else if (one)                                                                                      \
+            ncc_score_pmvs<MU_, false, 32, true><<<(int)blocks, 32, 0, s>>>(A, N);                         \
+        else                                                                                               \
+            ncc_score_pmvs<MU_, false, 32, false><<<(int)blocks, 32, 0, s>>>(A, N);                        \
         break;
     switch (mu) {
         PMVS_LAUNCH(3) PMVS_LAUNCH(5) PMVS_LAUNCH(7) PMVS_LAUNCH(9) PMVS_LAUNCH(11)

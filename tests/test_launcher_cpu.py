@@ -44,6 +44,69 @@ def test_celltable_matches_reference_semantics():
     assert len(pts) == 1
 
 
+def test_lazy_celltable_reconstructs_in_the_reference_scan_order(golden):
+    """The device expansion hands its patches over as record ARRAYS; CellTable.reconstruct_from_Q must return them
+    in exactly the order the reference's scan (MVS2.py:159-173: view, x-cell, y-cell, list position; every distinct
+    patch once) produces on a fully materialised Q_table -- without building any MyPatch object."""
+    import numpy as np
+    from mvs_b200 import MVS2, records
+    e = golden("dino12_expansion")
+    V = e["vis"].shape[1]
+    imgs = [np.zeros((240, 320, 3), np.uint8) + v for v in range(V)]
+    ns = int(e["n_seeds"])
+    keep = e["vis"].sum(1) > 0
+    idx = np.nonzero(keep)[0]
+    seeds, rest = idx[idx < ns], idx[idx >= ns]
+
+    def build():
+        ct = MVS2.CellTable(imgs, cell_size=2)
+        for k in seeds:                                            # seeds arrive as objects through fill_with_point
+            p = MVS2.MyPatch(e["c"][k], e["n"][k], int(e["ref"][k]),
+                             [[int(v), float(e["xy"][k, 0]), float(e["xy"][k, 1])] for v in np.nonzero(e["vis"][k])[0]],
+                             np.array([1, 2, 3]), None)
+            for hit in p.V:
+                ct.fill_with_point(hit[0], hit[1], hit[2], p)
+        recs = records.make_records(V, e["c"][rest], e["n"][rest], e["xy"][rest], e["avg"][rest], e["ref"][rest], e["vis"][rest],
+                                    px=np.stack([np.clip(e["xy"][rest, 0].astype(np.int32), 0, 319),
+                                                 np.clip(e["xy"][rest, 1].astype(np.int32), 0, 239)], 1))
+        half = len(recs) // 2                                      # two "rounds"
+        for part in (recs[:half], recs[half:]):
+            ct._add_records(part, MVS2._record_colors(part, imgs))
+        return ct
+    lazy = build()
+    pts_a, col_a = lazy.reconstruct_from_Q()
+    assert len(lazy._pending) == 2                                 # nothing was materialised
+    eager = build()
+    q = eager.Q_table                                              # materialises MyPatch objects
+    assert not eager._pending and sum(len(v) for v in q.values()) > 0
+    pts_b, col_b = eager.reconstruct_from_Q()
+    assert len(pts_a) == len(pts_b) == len(seeds) + len(rest)
+    assert np.array_equal(np.array(pts_a), np.array(pts_b))
+    assert np.array_equal(np.array(col_a), np.array(col_b))
+    # and the reference's own scan on the materialised table gives the same list
+    seen, want = set(), []
+    for v in range(V):
+        t = eager.table[v]
+        for i in range(t.shape[0]):
+            for j in range(t.shape[1]):
+                for p in q.get((v, i, j), []):
+                    if id(p) not in seen:
+                        seen.add(id(p))
+                        want.append(p.c)
+    assert np.array_equal(np.array(want), np.array(pts_b))
+
+
+def test_context_fingerprint_sees_pixel_edits():
+    import numpy as np
+    from mvs_b200 import MVS2
+    rng = np.random.default_rng(0)
+    imgs = [rng.integers(0, 255, (48, 64, 3)).astype(np.uint8) for _ in range(3)]
+    a = MVS2._fingerprint(imgs)
+    assert a == MVS2._fingerprint([im.copy() for im in imgs])
+    imgs[1][0, 5, 1] ^= 1                                          # first row: always sampled
+    assert MVS2._fingerprint(imgs) != a
+
+
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference not mounted")
 def test_launcher_runs_reference_main_up_to_the_device_boundary(tmp_path):
     import torch
