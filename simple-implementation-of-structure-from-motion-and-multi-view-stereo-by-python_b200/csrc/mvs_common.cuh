@@ -74,7 +74,7 @@ struct mvs_ctx {
     float* pmvs_off_host;                  // [V,2] tile origin of each view
     void* d_pmvs_tex;                      // [V] cudaTextureObject_t
     void* d_pmvs_off;                      // [V] float2
-    void* d_pmvs_camf;                     // [V] CamProjF
+    void* d_pmvs_camf;                     // cameras field-major: double [16][V] then float [13][V]
     CamProj* d_cam;       // [V]
     CamGeom* d_geom;      // [V]
     double* h_rrt;        // [V,9] host copy

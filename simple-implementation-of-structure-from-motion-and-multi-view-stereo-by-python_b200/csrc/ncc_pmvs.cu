@@ -30,12 +30,13 @@
 #define FULL 0xffffffffu
 #define PMVS_VAR_MIN (1e-3f / 65025.0f)        // oracle/mode_b.py VAR_MIN in (grey/255)^2
 
-// fp32 copy of one view's camera for the per-step increments
-struct __align__(16) CamProjF {
-    float r[9];
-    float fx, fy, cx, cy;
-    float pad[3];
-};
+// Cameras as the staging lanes read them: lane v stages view v, so the fields are stored FIELD-MAJOR
+// (structure of arrays): a warp-wide read of one field is one coalesced run.  With the 128-byte CamProj records
+// every such read touched 32 different lines -- ~14 data-pipe wavefronts per load, ~670 per hypothesis, more than
+// the shared-memory traffic of the whole kernel.
+//   cam64 [16][V] double: r0..r8, t0..t2, fx, fy, cx, cy        cam32 [13][V] float: r0..r8, fx, fy, cx, cy
+#define PMVS_CAM64_FIELDS 16
+#define PMVS_CAM32_FIELDS 13
 
 // Texture handles of the views, read with a warp-uniform index: a handle that is provably
 // uniform lets TLD4 take it from a uniform register (no per-lane "waterfall" loop).  One table
@@ -46,11 +47,16 @@ __constant__ float2 c_off[PMVS_MAX_VIEWS];         // tile origin of each view i
 
 struct PmvsArgs {
     const CamProj* cams;
-    const CamProjF* camsf;
+    const double* cam64;       // [PMVS_CAM64_FIELDS][V]
+    const float* cam32;        // [PMVS_CAM32_FIELDS][V]
     const cudaTextureObject_t* tex;
     const float2* off;         // [V] tile origin of each view inside its atlas
     int V, H, W;
     int flags;
+    int cam_stride;            // = V, the field pitch of cam64 / cam32.  A kernel argument of ITS OWN: when the staging
+                               // lanes' address arithmetic used A.V itself, ptxas kept A.V in a vector register and computed the
+                               // texture-handle index min(view, A.V - 1) there too -- the handle then lost its uniform register
+                               // and every TLD4 of the multi-atlas variants got a waterfall loop (tests/test_abi_cpu.py)
     int group;                 // hypotheses per selection set (<= 1: no selection)
     int bound;
     float thr;
@@ -201,14 +207,16 @@ __global__ void __launch_bounds__(32, MINB) ncc_score_pmvs(const PmvsArgs A, int
             // prepare view v for this hypothesis into slot `slot` (executed by one lane per view)
             auto stage_view = [&](int v, int slot) -> bool {
                 const int cam = reduce_a ? r : v;          // MVS2.py:68: the reference camera for every view
-                const CamProj& cv = A.cams[cam];
-                const CamProjF& cf = A.camsf[cam];
-                const double Xc = cv.r[0] * c0 + cv.r[1] * c1 + cv.r[2] * c2 + cv.t[0];
-                const double Yc = cv.r[3] * c0 + cv.r[4] * c1 + cv.r[5] * c2 + cv.t[1];
-                const double Zv = cv.r[6] * c0 + cv.r[7] * c1 + cv.r[8] * c2 + cv.t[2];
+                const double* c64 = A.cam64 + cam;
+                const float* c32 = A.cam32 + cam;
+                const int Vs = A.cam_stride;
+                const double cvfx = c64[12 * Vs], cvfy = c64[13 * Vs], cvcx = c64[14 * Vs], cvcy = c64[15 * Vs];
+                const double Xc = c64[0] * c0 + c64[1 * Vs] * c1 + c64[2 * Vs] * c2 + c64[9 * Vs];
+                const double Yc = c64[3 * Vs] * c0 + c64[4 * Vs] * c1 + c64[5 * Vs] * c2 + c64[10 * Vs];
+                const double Zv = c64[6 * Vs] * c0 + c64[7 * Vs] * c1 + c64[8 * Vs] * c2 + c64[11 * Vs];
                 ViewAffine va;
                 const double izd = 1.0 / Zv;
-                const double uc = (cv.fx * Xc + cv.cx * Zv) * izd, vc = (cv.fy * Yc + cv.cy * Zv) * izd;
+                const double uc = (cvfx * Xc + cvcx * Zv) * izd, vc = (cvfy * Yc + cvcy * Zv) * izd;
                 const double ucf = floor(uc), vcf = floor(vc);
                 // integer parts carry the view's tile origin inside the atlas and the +1 that addresses the
                 // centre of the 2x2 gather footprint, so a tap coordinate is iu + floor(.) with no further adds
@@ -217,17 +225,19 @@ __global__ void __launch_bounds__(32, MINB) ncc_score_pmvs(const PmvsArgs A, int
                 va.iv = (float)vcf + org.y + 1.0f; va.fv = (float)(vc - vcf);
                 const float Z0 = (float)Zv;
                 const float iZ0 = Z0 > 0.0f ? rcp_approx(Z0) : nanf("");   // behind the camera: every tap test fails on NaN
-                const float rx0 = cf.r[0] * ex[0] + cf.r[1] * ex[1] + cf.r[2] * ex[2];
-                const float rx1 = cf.r[3] * ex[0] + cf.r[4] * ex[1] + cf.r[5] * ex[2];
-                const float rx2 = cf.r[6] * ex[0] + cf.r[7] * ex[1] + cf.r[8] * ex[2];
-                const float ry0 = cf.r[0] * ey[0] + cf.r[1] * ey[1] + cf.r[2] * ey[2];
-                const float ry1 = cf.r[3] * ey[0] + cf.r[4] * ey[1] + cf.r[5] * ey[2];
-                const float ry2 = cf.r[6] * ey[0] + cf.r[7] * ey[1] + cf.r[8] * ey[2];
+                const float f0 = c32[0], f1 = c32[1 * Vs], f2 = c32[2 * Vs], f3 = c32[3 * Vs], f4 = c32[4 * Vs], f5 = c32[5 * Vs],
+                            f6 = c32[6 * Vs], f7 = c32[7 * Vs], f8 = c32[8 * Vs], cffx = c32[9 * Vs], cffy = c32[10 * Vs];
+                const float rx0 = f0 * ex[0] + f1 * ex[1] + f2 * ex[2];
+                const float rx1 = f3 * ex[0] + f4 * ex[1] + f5 * ex[2];
+                const float rx2 = f6 * ex[0] + f7 * ex[1] + f8 * ex[2];
+                const float ry0 = f0 * ey[0] + f1 * ey[1] + f2 * ey[2];
+                const float ry1 = f3 * ey[0] + f4 * ey[1] + f5 * ey[2];
+                const float ry2 = f6 * ey[0] + f7 * ey[1] + f8 * ey[2];
                 // hx.X - uc*hx.Z = step*(fx*rx0 + (cx - uc)*rx2): the principal point cancels against uc
-                const float du = (float)(cv.cx - uc), dv = (float)(cv.cy - vc);
+                const float du = (float)(cvcx - uc), dv = (float)(cvcy - vc);
                 const float hxZ = step * rx2, hyZ = step * ry2;
-                const float gxu = step * fmaf(du, rx2, cf.fx * rx0), gyu = step * fmaf(du, ry2, cf.fx * ry0);
-                const float gxv = step * fmaf(dv, rx2, cf.fy * rx1), gyv = step * fmaf(dv, ry2, cf.fy * ry1);
+                const float gxu = step * fmaf(du, rx2, cffx * rx0), gyu = step * fmaf(du, ry2, cffx * ry0);
+                const float gxv = step * fmaf(dv, rx2, cffy * rx1), gyv = step * fmaf(dv, ry2, cffy * ry1);
                 va.ex = hxZ * iZ0; va.ey = hyZ * iZ0;
                 va.gxu = gxu * iZ0; va.gyu = gyu * iZ0;
                 va.gxv = gxv * iZ0; va.gyv = gyv * iZ0;
@@ -474,7 +484,8 @@ int mvs_pmvs_prepare(mvs_ctx* ctx, cudaStream_t s) {
     int rc = MVS_OK;
     uint8_t* d_planar = nullptr;
     CamProj* hp = nullptr;
-    CamProjF* hf = nullptr;
+    double* h64 = nullptr;
+    float* h32 = nullptr;
     cudaTextureObject_t* htex = nullptr;
     int max_w = 0, max_h = 0;
     if (cudaDeviceGetAttribute(&max_w, cudaDevAttrMaxTexture2DGatherWidth, ctx->device) != cudaSuccess ||
@@ -503,8 +514,9 @@ int mvs_pmvs_prepare(mvs_ctx* ctx, cudaStream_t s) {
     ctx->pmvs_tex_host = (cudaTextureObject_t*)calloc(V, sizeof(cudaTextureObject_t));
     ctx->pmvs_off_host = (float*)calloc(2 * (size_t)V, sizeof(float));
     hp = (CamProj*)malloc(sizeof(CamProj) * V);
-    hf = (CamProjF*)calloc(V, sizeof(CamProjF));
-    if (!ctx->pmvs_arrays || !ctx->pmvs_atlas_tex || !ctx->pmvs_tex_host || !ctx->pmvs_off_host || !hp || !hf) {
+    h64 = (double*)calloc((size_t)PMVS_CAM64_FIELDS * V, sizeof(double));
+    h32 = (float*)calloc((size_t)PMVS_CAM32_FIELDS * V, sizeof(float));
+    if (!ctx->pmvs_arrays || !ctx->pmvs_atlas_tex || !ctx->pmvs_tex_host || !ctx->pmvs_off_host || !hp || !h64 || !h32) {
         rc = MVS_ERR_NOMEM;
         goto done;
     }
@@ -559,19 +571,29 @@ int mvs_pmvs_prepare(mvs_ctx* ctx, cudaStream_t s) {
     }
     if (cudaMemcpy(hp, ctx->d_cam, sizeof(CamProj) * V, cudaMemcpyDeviceToHost) != cudaSuccess) { rc = MVS_ERR_CUDA; goto done; }
     for (int v = 0; v < V; ++v) {
-        for (int i = 0; i < 9; ++i) hf[v].r[i] = (float)hp[v].r[i];
-        hf[v].fx = (float)hp[v].fx; hf[v].fy = (float)hp[v].fy; hf[v].cx = (float)hp[v].cx; hf[v].cy = (float)hp[v].cy;
+        for (int i = 0; i < 9; ++i) {
+            h64[(size_t)i * V + v] = hp[v].r[i];
+            h32[(size_t)i * V + v] = (float)hp[v].r[i];
+        }
+        for (int i = 0; i < 3; ++i) h64[(size_t)(9 + i) * V + v] = hp[v].t[i];
+        const double k4[4] = {hp[v].fx, hp[v].fy, hp[v].cx, hp[v].cy};
+        for (int i = 0; i < 4; ++i) {
+            h64[(size_t)(12 + i) * V + v] = k4[i];
+            h32[(size_t)(9 + i) * V + v] = (float)k4[i];
+        }
     }
     if (cudaMalloc(&ctx->d_pmvs_off, sizeof(float) * 2 * V) != cudaSuccess ||
         cudaMalloc(&ctx->d_pmvs_tex, sizeof(cudaTextureObject_t) * V) != cudaSuccess ||
-        cudaMalloc(&ctx->d_pmvs_camf, sizeof(CamProjF) * V) != cudaSuccess) {
+        cudaMalloc(&ctx->d_pmvs_camf, (sizeof(double) * PMVS_CAM64_FIELDS + sizeof(float) * PMVS_CAM32_FIELDS) * (size_t)V) != cudaSuccess) {
         cudaGetLastError();
         rc = MVS_ERR_NOMEM;
         goto done;
     }
     if (cudaMemcpyAsync(ctx->d_pmvs_off, ctx->pmvs_off_host, sizeof(float) * 2 * V, cudaMemcpyHostToDevice, s) != cudaSuccess ||
         cudaMemcpyAsync(ctx->d_pmvs_tex, htex, sizeof(cudaTextureObject_t) * V, cudaMemcpyHostToDevice, s) != cudaSuccess ||
-        cudaMemcpyAsync(ctx->d_pmvs_camf, hf, sizeof(CamProjF) * V, cudaMemcpyHostToDevice, s) != cudaSuccess ||
+        cudaMemcpyAsync(ctx->d_pmvs_camf, h64, sizeof(double) * PMVS_CAM64_FIELDS * (size_t)V, cudaMemcpyHostToDevice, s) != cudaSuccess ||
+        cudaMemcpyAsync((double*)ctx->d_pmvs_camf + (size_t)PMVS_CAM64_FIELDS * V, h32, sizeof(float) * PMVS_CAM32_FIELDS * (size_t)V,
+                        cudaMemcpyHostToDevice, s) != cudaSuccess ||
         cudaStreamSynchronize(s) != cudaSuccess) {
         mvs_set_error("Mode B set-up: upload failed: %s", cudaGetErrorString(cudaGetLastError()));
         rc = MVS_ERR_CUDA;
@@ -585,7 +607,8 @@ int mvs_pmvs_prepare(mvs_ctx* ctx, cudaStream_t s) {
 done:
     if (d_planar) cudaFree(d_planar);
     free(hp);
-    free(hf);
+    free(h64);
+    free(h32);
     return rc;
 }
 
@@ -639,10 +662,11 @@ int mvs_launch_score_pmvs(mvs_ctx* ctx, int64_t N, const double* c, const double
     }
     PmvsArgs A;
     A.cams = ctx->d_cam;
-    A.camsf = (const CamProjF*)ctx->d_pmvs_camf;
+    A.cam64 = (const double*)ctx->d_pmvs_camf;
+    A.cam32 = (const float*)((const double*)ctx->d_pmvs_camf + (size_t)PMVS_CAM64_FIELDS * ctx->V);
     A.tex = (const cudaTextureObject_t*)ctx->d_pmvs_tex;
     A.off = (const float2*)ctx->d_pmvs_off;
-    A.V = ctx->V; A.H = ctx->H; A.W = ctx->W;
+    A.V = ctx->V; A.H = ctx->H; A.W = ctx->W; A.cam_stride = ctx->V;
     A.flags = flags; A.group = group; A.bound = bound; A.thr = (float)thr;
     A.c = c; A.nrm = nrm; A.ref = ref; A.cand = cand;
     A.vis_out = vis; A.avg_out = avg; A.count_out = count; A.xy_out = xy; A.ncc_out = ncc;
