@@ -133,6 +133,12 @@ __global__ void __launch_bounds__(32, MINB) ncc_score_pmvs(const PmvsArgs A, int
     constexpr int VSTRIDE = ((MU * MU + 29) / 32) * 32 + 2;
     __shared__ float s_val[16][VSTRIDE];
     __shared__ float s_dref[MU * MU];                      // pivot-shifted samples of the reference view
+    // Projection of the CURRENT centre through the first 64 views (uc, vc in fp64, depth), kept across consecutive
+    // hypotheses with the same centre and reference view -- the normals of one depth in a depth x normal set -- so
+    // that the fp64 part of the staging (12 loads, 3 dot products, a division) runs once per centre, not per normal.
+    // Lane l only ever reads back what it wrote itself (views l and 32 + l): no synchronisation.
+    __shared__ double s_cuc[64], s_cvc[64];
+    __shared__ float s_czv[64];
 
     // ONE_ATLAS (every BASELINE shape up to 128 x 1080p): all views are tiles of one texture, so its handle is read
     // from the constant bank ONCE instead of once per view (LDCU + index clamp + R2UR per gather batch entry)
@@ -163,6 +169,9 @@ __global__ void __launch_bounds__(32, MINB) ncc_score_pmvs(const PmvsArgs A, int
     for (int64_t set = warp0; set < n_sets; set += nwarps) {
         float best_key = -INFINITY;
         int best_i = -1;
+        double pc0 = 0.0, pc1 = 0.0, pc2 = 0.0;            // centre / reference view whose projections are cached
+        int pr = -1;
+        unsigned cached = 0u;                              // bit b: the cache of view block b belongs to (pc, pr)
         for (int gi = 0; gi < group; ++gi) {
             const int64_t h = set * group + gi;
             if (h >= N) break;
@@ -205,25 +214,42 @@ __global__ void __launch_bounds__(32, MINB) ncc_score_pmvs(const PmvsArgs A, int
             }
 
             // prepare view v for this hypothesis into slot `slot` (executed by one lane per view)
-            auto stage_view = [&](int v, int slot) -> bool {
+            // cidx >= 0: cache slot of this (lane, view block); use_cache: that slot holds this centre's projection
+            auto stage_view = [&](int v, int slot, int cidx, bool use_cache) -> bool {
                 const int cam = reduce_a ? r : v;          // MVS2.py:68: the reference camera for every view
                 const double* c64 = A.cam64 + cam;
                 const float* c32 = A.cam32 + cam;
                 const int Vs = A.cam_stride;
-                const double cvfx = c64[12 * Vs], cvfy = c64[13 * Vs], cvcx = c64[14 * Vs], cvcy = c64[15 * Vs];
-                const double Xc = c64[0] * c0 + c64[1 * Vs] * c1 + c64[2 * Vs] * c2 + c64[9 * Vs];
-                const double Yc = c64[3 * Vs] * c0 + c64[4 * Vs] * c1 + c64[5 * Vs] * c2 + c64[10 * Vs];
-                const double Zv = c64[6 * Vs] * c0 + c64[7 * Vs] * c1 + c64[8 * Vs] * c2 + c64[11 * Vs];
+                const double cvcx = c64[14 * Vs], cvcy = c64[15 * Vs];
+                double uc, vc;
+                float Zvf;
+                if (use_cache) {
+                    uc = s_cuc[cidx];
+                    vc = s_cvc[cidx];
+                    Zvf = s_czv[cidx];
+                } else {
+                    const double cvfx = c64[12 * Vs], cvfy = c64[13 * Vs];
+                    const double Xc = c64[0] * c0 + c64[1 * Vs] * c1 + c64[2 * Vs] * c2 + c64[9 * Vs];
+                    const double Yc = c64[3 * Vs] * c0 + c64[4 * Vs] * c1 + c64[5 * Vs] * c2 + c64[10 * Vs];
+                    const double Zv = c64[6 * Vs] * c0 + c64[7 * Vs] * c1 + c64[8 * Vs] * c2 + c64[11 * Vs];
+                    const double izd = 1.0 / Zv;
+                    uc = (cvfx * Xc + cvcx * Zv) * izd;
+                    vc = (cvfy * Yc + cvcy * Zv) * izd;
+                    Zvf = (float)Zv;
+                    if (cidx >= 0) {
+                        s_cuc[cidx] = uc;
+                        s_cvc[cidx] = vc;
+                        s_czv[cidx] = Zvf;
+                    }
+                }
                 ViewAffine va;
-                const double izd = 1.0 / Zv;
-                const double uc = (cvfx * Xc + cvcx * Zv) * izd, vc = (cvfy * Yc + cvcy * Zv) * izd;
                 const double ucf = floor(uc), vcf = floor(vc);
                 // integer parts carry the view's tile origin inside the atlas and the +1 that addresses the
                 // centre of the 2x2 gather footprint, so a tap coordinate is iu + floor(.) with no further adds
                 const float2 org = A.off[v];
                 va.iu = (float)ucf + org.x + 1.0f; va.fu = (float)(uc - ucf);
                 va.iv = (float)vcf + org.y + 1.0f; va.fv = (float)(vc - vcf);
-                const float Z0 = (float)Zv;
+                const float Z0 = Zvf;
                 const float iZ0 = Z0 > 0.0f ? rcp_approx(Z0) : nanf("");   // behind the camera: every tap test fails on NaN
                 const float f0 = c32[0], f1 = c32[1 * Vs], f2 = c32[2 * Vs], f3 = c32[3 * Vs], f4 = c32[4 * Vs], f5 = c32[5 * Vs],
                             f6 = c32[6 * Vs], f7 = c32[7 * Vs], f8 = c32[8 * Vs], cffx = c32[9 * Vs], cffy = c32[10 * Vs];
@@ -299,11 +325,17 @@ __global__ void __launch_bounds__(32, MINB) ncc_score_pmvs(const PmvsArgs A, int
                 if (hyp_ok) {                              // uniform across the warp
                     // ---- stage this block's 32 views (one lane each); block 0 also stages the reference view
                     __syncwarp();
-                    const bool safe = stage_view(min(w32 * 32 + lane, A.V - 1), lane);   // lanes past the last view shadow it
+                    const bool same_c = !reduce_a && w32 < 2 && ((cached >> w32) & 1u) && r == pr && c0 == pc0 && c1 == pc1 && c2 == pc2;
+                    const bool safe = stage_view(min(w32 * 32 + lane, A.V - 1), lane, w32 < 2 ? w32 * 32 + lane : -1, same_c);   // lanes past the last view shadow it
+                    if (w32 < 2 && !same_c) {              // (uniform) this block's cache now belongs to the current centre
+                        if (!(r == pr && c0 == pc0 && c1 == pc1 && c2 == pc2)) cached = 0u;
+                        pc0 = c0; pc1 = c1; pc2 = c2; pr = r;
+                        cached |= 1u << w32;
+                    }
                     // one vote per half: every view of the half safe -> its taps skip the bounds tests
                     safe_lo = __all_sync(FULL, safe || lane >= 16);
                     safe_hi = __all_sync(FULL, safe || lane < 16);
-                    if (w32 == 0 && r >= 32 && lane == 0) stage_view(r, 32);
+                    if (w32 == 0 && r >= 32 && lane == 0) stage_view(r, 32, -1, false);
                     __syncwarp();
                     if (w32 == 0) {
                         // ---- the reference view's own samples

@@ -147,6 +147,11 @@ def test_on_chip_argmax_over_hypothesis_sets(built_lib):
     with mvs_b200.MvsContext(rgb, K, R, t, Rrt=cams.R) as ctx:
         full = ctx.score_pmvs_host(c, nrm, ref, min_ncc=0.6, mu=5, group=G, bound=2)
         only = ctx.score_pmvs_host(c, nrm, ref, min_ncc=0.6, mu=5, group=G, bound=2, per_hypothesis=False)
+        # inside a set, hypotheses with the same centre reuse the cached fp64 projections of the centre; scored one
+        # by one (group 1: nothing is carried over) every per-hypothesis result must be bit-identical
+        plain = ctx.score_pmvs_host(c, nrm, ref, min_ncc=0.6, mu=5)
+        for k in ("vis_mask", "avg", "count"):
+            assert np.array_equal(plain[k], full[k]), k
         bi, ba = ctx.select_best_device(torch.from_numpy(full["avg"]).cuda(), torch.from_numpy(full["count"]).cuda(), G, 2)
         torch.cuda.synchronize()
     want_i, want_a = mode_b.select_best(full["avg"].astype(np.float32), full["count"], 2, G)
