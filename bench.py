@@ -768,9 +768,7 @@ def run_dino_rounds(args):
     e2e_t = []
     try:
         for i in range(3):
-            if MVS2._CTX["ctx"] is not None:                  # a fresh context: the image upload is inside the timed region
-                MVS2._CTX["ctx"].close()
-            MVS2._CTX.update(key=None, ctx=None, imgs=None)
+            MVS2.invalidate_context()                         # a fresh context: the image upload is inside the timed region
             t0 = time.perf_counter()
             with contextlib.redirect_stdout(io.StringIO()):
                 MVS2.DensePointsWithMVS2(imgs, gs, a)

@@ -25,7 +25,7 @@ from .ply import export2ply
 from .records import make_records, unpack_vis
 
 __all__ = ["MyPatchHeapSort", "MyMatch", "ctNcc", "MyPatch", "CellTable", "DensePointsWithMVS2", "is_patch_neighbor",
-           "ray_plane_intersection", "patch_expansion"]
+           "ray_plane_intersection", "patch_expansion"]        # (invalidate_context is this module's own helper, not exported by *)
 
 
 # ---------------------------------------------------------------------------------------
@@ -62,7 +62,7 @@ def _roundtrip(R):
     return np.stack([cv2.Rodrigues(cv2.Rodrigues(r)[0])[0] for r in R])
 
 
-_CTX = {"key": None, "ctx": None, "imgs": None}
+_CTX = {"key": None, "ctx": None, "imgs": None, "pars": None}
 
 
 def _fingerprint(imgs):
@@ -80,27 +80,44 @@ def _fingerprint(imgs):
     return h
 
 
+def invalidate_context():
+    """Drop the cached GPU context (call after editing the pixels of a cached image list IN PLACE)."""
+    if _CTX["ctx"] is not None:
+        _CTX["ctx"].close()
+    _CTX.update(key=None, ctx=None, imgs=None, pars=None)
+
+
 def _context(imgs, par_K, par_r, par_t):
-    """The image stack and cameras live on the GPU once per (image list, cameras).  The cache keeps a
-    strong reference to the list (its id() cannot be recycled while cached) and keys on a content
-    fingerprint; MVS_CTX_STRICT=1 fingerprints every pixel."""
+    """The image stack and cameras live on the GPU once per (image list, cameras).
+    * The cache keeps a STRONG reference to the list, so its id() cannot be recycled by a new list while cached.
+    * A list object seen for the first time is keyed on a content fingerprint as well (a different list with
+      equal shape and cameras never reuses stale pixels).
+    * The same list object again takes the fast path (identity + cameras; 70 us per call instead of 0.9 ms for
+      re-fingerprinting 48 images): pixels edited IN PLACE are then not noticed -- call invalidate_context(), or
+      set MVS_CTX_STRICT=1 to fingerprint every pixel on every call."""
     V = len(imgs)
+    strict = bool(os.environ.get("MVS_CTX_STRICT"))
+    pars = (par_K, par_r, par_t)
+    if (not strict and _CTX["ctx"] is not None and imgs is _CTX["imgs"] and _CTX.get("pars") is not None and
+            all(a is b for a, b in zip(pars, _CTX["pars"]))):
+        return _CTX["ctx"]                                   # same list object, same parameter dicts
     K, R, t = _stack_pars(par_K, par_r, par_t, V)
-    if os.environ.get("MVS_CTX_STRICT"):
+    if strict:
         import zlib
         fp = 0
         for im in imgs:
             fp = zlib.crc32(np.ascontiguousarray(im).tobytes(), fp)
     else:
         fp = _fingerprint(imgs)
-    key = (id(imgs), V, imgs[0].shape, fp, K.tobytes(), R.tobytes(), t.tobytes())
+    key = (V, imgs[0].shape, fp, K.tobytes(), R.tobytes(), t.tobytes())
     if _CTX["key"] != key:
         if _CTX["ctx"] is not None:
             _CTX["ctx"].close()
         device = int(os.environ.get("MVS_DEVICE", os.environ.get("LOCAL_RANK", "0")))
         _CTX["ctx"] = MvsContext(imgs, K, R, t, Rrt=_roundtrip(R), device=device)
         _CTX["key"] = key
-        _CTX["imgs"] = imgs
+    _CTX["imgs"] = imgs
+    _CTX["pars"] = pars
     return _CTX["ctx"]
 
 

@@ -32,17 +32,19 @@ __global__ void __launch_bounds__(256)
                 int32_t* __restrict__ key, int32_t* __restrict__ rank, uint32_t* __restrict__ anchor,
                 uint64_t* __restrict__ vis_out, double* __restrict__ avg_out, int32_t* __restrict__ count_out,
                 double* __restrict__ xy_out, float* __restrict__ ncc_out, int cams_in_smem) {
-    // cameras go to shared memory once per CTA: every thread reads the 128-byte record of ITS reference
-    // view (32 different L1 lines per warp instruction when read from global memory)
+    // cameras go to shared memory once per CTA: every thread reads the 128-byte record of ITS reference view.  The rows
+    // are padded to 17 doubles: with the natural 16-double pitch field k of EVERY view falls on the same two banks, and a
+    // warp whose lanes have ~24 different reference views paid a ~24-way bank conflict on each of its 16 field reads.
+    constexpr int PITCH = 17;
     extern __shared__ __align__(16) unsigned char s_cam_raw[];
-    const CamProj* cam_src = cams;
+    const double* s_cam = nullptr;
     if (cams_in_smem) {
-        CamProj* s_cam = reinterpret_cast<CamProj*>(s_cam_raw);
+        double* dst = reinterpret_cast<double*>(s_cam_raw);
         const double* src = reinterpret_cast<const double*>(cams);
-        double* dst = reinterpret_cast<double*>(s_cam);
-        for (int i = threadIdx.x; i < V * (int)(sizeof(CamProj) / sizeof(double)); i += blockDim.x) dst[i] = src[i];
+        constexpr int F = (int)(sizeof(CamProj) / sizeof(double));      // 16
+        for (int i = threadIdx.x; i < V * F; i += blockDim.x) dst[(i / F) * PITCH + (i % F)] = src[i];
         __syncthreads();
-        cam_src = s_cam;
+        s_cam = dst;
     }
     const int mw = (V + 63) >> 6;
     for (int64_t h = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; h < N; h += (int64_t)gridDim.x * blockDim.x) {
@@ -51,7 +53,18 @@ __global__ void __launch_bounds__(256)
         int row = 0, col = 0;
         bool valid = false;
         if (r >= 0 && r < V) {
-            project_ref(cam_src[r], __ldg(c + 3 * h), __ldg(c + 3 * h + 1), __ldg(c + 3 * h + 2), x, y);
+            if (s_cam) {
+                CamProj cam;
+                const double* rowp = s_cam + r * PITCH;
+#pragma unroll
+                for (int i = 0; i < 9; ++i) cam.r[i] = rowp[i];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) cam.t[i] = rowp[9 + i];
+                cam.fx = rowp[12]; cam.fy = rowp[13]; cam.cx = rowp[14]; cam.cy = rowp[15];
+                project_ref(cam, __ldg(c + 3 * h), __ldg(c + 3 * h + 1), __ldg(c + 3 * h + 2), x, y);
+            } else {
+                project_ref(cams[r], __ldg(c + 3 * h), __ldg(c + 3 * h + 1), __ldg(c + 3 * h + 2), x, y);
+            }
             valid = window_anchor(x, y, H, W, wid, row, col);
         }
         if (xy_out) {
@@ -111,7 +124,7 @@ int mvs_bin_hypotheses(mvs_ctx* ctx, int64_t N, const double* c, const int32_t* 
     int64_t blocks = (N + 255) / 256;
     const int64_t cap = (int64_t)ctx->sm_count * 16;
     if (blocks > cap) blocks = cap;
-    const size_t cam_bytes = sizeof(CamProj) * (size_t)ctx->V;
+    const size_t cam_bytes = 17 * sizeof(double) * (size_t)ctx->V;      // padded rows, see bin_project
     const int cams_in_smem = cam_bytes <= 48 * 1024 && N >= 4096;      // up to 384 views; tiny batches skip the staging
     bin_project<<<(int)blocks, 256, cams_in_smem ? cam_bytes : 0, s>>>(ctx->d_cam, ctx->V, ctx->H, ctx->W, wid, N, c, ref, tiles_x,
                                                                       n_tiles, sort ? ctx->d_bin_hist : nullptr, ctx->d_bin_key,
