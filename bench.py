@@ -357,7 +357,7 @@ def run_b200(args):
         if world > 1:
             import torch.distributed._symmetric_memory as symm_mem
             inbox = symm_mem.empty(nbytes, dtype=torch.uint8, device=dev)
-            flags = symm_mem.empty(world, dtype=torch.int64, device=dev)
+            flags = symm_mem.empty(world + 1, dtype=torch.int64, device=dev)      # one flag per peer + this GPU's epoch counter
             flags.zero_()
             h_in = symm_mem.rendezvous(inbox, dist.group.WORLD)
             h_fl = symm_mem.rendezvous(flags, dist.group.WORLD)

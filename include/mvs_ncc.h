@@ -334,10 +334,11 @@ int mvs_publish_accepted(mvs_ctx* ctx, int64_t N, const uint64_t* vis_mask, cons
 
 /*
  * Device-side barrier across the GPUs of the box: one tiny kernel, no host round trip, capturable in a
- * CUDA graph.  peer_flags: HOST array of `world` DEVICE pointers, entry g = GPU g's array of `world`
- * uint64 flags (zero-initialised by the caller before the first barrier) as mapped into this process.
- * Every context must call it the same number of times.  A rank that waits ~4 s for a peer gives up and
- * raises a sticky error that mvs_p2p_barrier_failed reports (it never hangs the GPU).
+ * CUDA graph.  peer_flags: HOST array of `world` DEVICE pointers, entry g = GPU g's array of `world + 1`
+ * uint64 words (slots 0..world-1: one flag per peer, slot world: that GPU's own epoch counter; ALL zero-initialised
+ * by the caller before the first barrier) as mapped into this process.  Every rank must call it the same number of
+ * times on the same arrays.  A rank that waits ~15 s for a peer gives up and raises a sticky error that
+ * mvs_p2p_barrier_failed reports (it never hangs the GPU).
  */
 int mvs_p2p_barrier(mvs_ctx* ctx, void* const* peer_flags, int rank, int world, void* stream);
 int mvs_p2p_barrier_failed(mvs_ctx* ctx, void* stream);

@@ -227,7 +227,7 @@ extern "C" int mvs_publish_accepted(mvs_ctx* ctx, int64_t N, const uint64_t* vis
 // GPU's flag array (release, system scope, after a system-wide fence that orders the publish kernels'
 // stores before it) and waits until all slots of its own array reached the epoch.  One tiny kernel, no
 // host round trip, capturable in a CUDA graph (the epoch lives in device memory).  A rank that waits
-// longer than ~4 s gives up and raises the context's error flag instead of hanging the GPU.
+// longer than ~15 s gives up and raises the context's error flag instead of hanging the GPU.
 // ---------------------------------------------------------------------------------------
 struct PeerFlags {
     unsigned long long* flags[MVS_MAX_PEERS];
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(32) p2p_barrier(const PeerFlags P, unsigned lo
         for (;;) {
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
             if (seen >= epoch) break;
-            if (clock64() - t0 > 8000000000ll) {           // ~4 s at 2 GHz: a peer is gone
+            if (clock64() - t0 > 30000000000ll) {          // ~15 s at 2 GHz: a peer is gone
                 *err = 1;
                 break;
             }
@@ -280,8 +280,9 @@ extern "C" int mvs_p2p_barrier(mvs_ctx* ctx, void* const* peer_flags, int rank, 
         if (!peer_flags[d]) { mvs_set_error("mvs_p2p_barrier: null flag pointer %d", d); return MVS_ERR_ARG; }
         P.flags[d] = (unsigned long long*)peer_flags[d];
     }
-    p2p_barrier<<<1, 32, 0, (cudaStream_t)stream>>>(P, (unsigned long long*)ctx->d_barrier_state,
-                                                    (int*)((uint8_t*)ctx->d_barrier_state + 8));
+    // the epoch counter lives in slot `world` of this GPU's OWN flag array: it is zeroed together with the flags, so
+    // the ranks' epochs agree by construction whatever else the contexts did before
+    p2p_barrier<<<1, 32, 0, (cudaStream_t)stream>>>(P, P.flags[rank] + world, (int*)((uint8_t*)ctx->d_barrier_state + 8));
     ctx->launches++;
     MVS_CUDA_CHECK(cudaGetLastError());
     return MVS_OK;

@@ -135,7 +135,7 @@ class DeviceBackend:
         t = self.torch
         nbytes = int(self.lib.mvs_exchange_bytes(self.ctx._h, world, capacity))
         inbox = symm_mem.empty(nbytes, dtype=t.uint8, device=self.device)
-        flags = symm_mem.empty(world, dtype=t.int64, device=self.device)
+        flags = symm_mem.empty(world + 1, dtype=t.int64, device=self.device)     # one flag per peer + this GPU's epoch counter
         flags.zero_()
         h = symm_mem.rendezvous(inbox, group)
         h2 = symm_mem.rendezvous(flags, group)

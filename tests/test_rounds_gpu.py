@@ -175,11 +175,12 @@ def test_publish_and_barrier_single_gpu(golden, built_lib):
             rc = lib.mvs_publish_accepted(ctx._h, N, C.c_void_p(vis.data_ptr()), C.c_void_p(avg.data_ptr()), C.c_void_p(count.data_ptr()),
                                           C.c_void_p(gate.data_ptr()), 3, tab, 0, 1, cap, parity, st)
             assert rc == 0, lib.mvs_last_error()
-        flags = torch.zeros(1, dtype=torch.int64, device=dev)
+        flags = torch.zeros(2, dtype=torch.int64, device=dev)                     # world flags + the epoch counter
         ftab = (C.c_void_p * 1)(flags.data_ptr())
         assert lib.mvs_p2p_barrier(ctx._h, ftab, 0, 1, st) == 0
+        assert lib.mvs_p2p_barrier(ctx._h, ftab, 0, 1, st) == 0
         torch.cuda.synchronize()
-        assert lib.mvs_p2p_barrier_failed(ctx._h, st) == 0 and int(flags.item()) == 1
+        assert lib.mvs_p2p_barrier_failed(ctx._h, st) == 0 and flags.tolist() == [2, 2]
         raw = inbox.cpu().numpy()
         half = nbytes // 2
         keep = (count.cpu().numpy() >= 3) & (gate.cpu().numpy() != 0)
