@@ -58,62 +58,60 @@ __device__ __forceinline__ bool pass_flag(const int32_t* count, const uint8_t* g
     return i < N && count[i] >= bound && (gate == nullptr || gate[i] != 0);
 }
 
-__global__ void __launch_bounds__(256) publish_count(const int32_t* __restrict__ count, const uint8_t* __restrict__ gate,
-                                                     int bound, int64_t N, int32_t* __restrict__ tile_counts) {
+// Per-tile counts of passed candidates AND, in the CTA that finishes last (ticket counter), the exclusive scan of the
+// tile counts + the header {kept, n} to every inbox: one launch instead of two.
+__global__ void __launch_bounds__(256)
+    publish_count_scan(const int32_t* __restrict__ count, const uint8_t* __restrict__ gate, int bound, int64_t N,
+                       int32_t* __restrict__ tile_counts, int T, const PeerInbox P, unsigned* __restrict__ ticket) {
     __shared__ int warp_sum[8];
+    __shared__ bool s_last;
+    __shared__ long long s_carry;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t base = (int64_t)blockIdx.x * XTILE;
     int k = 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) k += pass_flag(count, gate, bound, base + j * 256 + threadIdx.x, N) ? 1 : 0;
     k = __reduce_add_sync(FULL, k);
-    if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = k;
+    if (lane == 0) warp_sum[w] = k;
     __syncthreads();
     if (threadIdx.x == 0) {
-        int s = 0;
-        for (int w = 0; w < 8; ++w) s += warp_sum[w];
-        tile_counts[blockIdx.x] = s;
+        int sum = 0;
+        for (int q = 0; q < 8; ++q) sum += warp_sum[q];
+        if ((int)blockIdx.x < T) tile_counts[blockIdx.x] = sum;
+        __threadfence();
+        s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+        s_carry = 0;
     }
-}
-
-// single CTA: exclusive scan of the tile counts in place; header {kept, n} to every inbox
-__global__ void __launch_bounds__(1024) publish_scan(int32_t* __restrict__ tile_counts, int T, int64_t N, const PeerInbox P) {
-    __shared__ int64_t carry;
-    __shared__ int wsum[32];
-    if (threadIdx.x == 0) carry = 0;
     __syncthreads();
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int base = 0; base < T; base += 1024) {
-        const int i = base + threadIdx.x;
+    if (!s_last) return;
+    __threadfence();                                       // the other CTAs' counts are visible
+    for (int b0 = 0; b0 < T; b0 += 256) {
+        const int i = b0 + threadIdx.x;
         const int v = (i < T) ? tile_counts[i] : 0;
         int x = v;
 #pragma unroll
-        for (int s = 1; s < 32; s <<= 1) {
-            const int y = __shfl_up_sync(FULL, x, s);
-            if (lane >= s) x += y;
+        for (int sft = 1; sft < 32; sft <<= 1) {
+            const int y = __shfl_up_sync(FULL, x, sft);
+            if (lane >= sft) x += y;
         }
-        if (lane == 31) wsum[w] = x;
+        if (lane == 31) warp_sum[w] = x;
         __syncthreads();
-        if (w == 0) {
-            int ws = wsum[lane];
-#pragma unroll
-            for (int s = 1; s < 32; s <<= 1) {
-                const int y = __shfl_up_sync(FULL, ws, s);
-                if (lane >= s) ws += y;
-            }
-            wsum[lane] = ws;
+        int before = 0, total = 0;
+        for (int q = 0; q < 8; ++q) {
+            if (q < w) before += warp_sum[q];
+            total += warp_sum[q];
         }
+        if (i < T) tile_counts[i] = (int32_t)(s_carry + before + (x - v));
         __syncthreads();
-        const int64_t excl = carry + (w > 0 ? wsum[w - 1] : 0) + (x - v);
-        if (i < T) tile_counts[i] = (int32_t)excl;
-        __syncthreads();
-        if (threadIdx.x == 1023) carry = excl + v;
+        if (threadIdx.x == 0) s_carry += total;
         __syncthreads();
     }
     if (threadIdx.x < P.world) {
         int64_t* hdr = reinterpret_cast<int64_t*>(P.base[threadIdx.x]);
-        hdr[0] = carry;
+        hdr[0] = s_carry;
         hdr[1] = N;
     }
+    if (threadIdx.x == 0) *ticket = 0u;                    // ready for the next launch
 }
 
 // words + entries of one tile of XTILE candidates to every inbox
@@ -189,11 +187,11 @@ int mvs_launch_publish(mvs_ctx* ctx, int64_t N, const uint64_t* vis, const doubl
     int rc;
     if ((rc = mvs_ensure((void**)&ctx->d_tiles, &ctx->tile_bytes, sizeof(int32_t) * (size_t)(T + 1), "publish scratch")) != MVS_OK)
         return rc;
-    if (T > 0) {
-        publish_count<<<T, 256, 0, s>>>(count, gate, bound, N, ctx->d_tiles);
-        ctx->launches++;
+    if (!ctx->d_ticket) {
+        MVS_CUDA_CHECK(cudaMalloc(&ctx->d_ticket, 64));
+        MVS_CUDA_CHECK(cudaMemsetAsync(ctx->d_ticket, 0, 64, s));
     }
-    publish_scan<<<1, 1024, 0, s>>>(ctx->d_tiles, T, N, P);    // T == 0: publishes an empty shard
+    publish_count_scan<<<T > 0 ? T : 1, 256, 0, s>>>(count, gate, bound, N, ctx->d_tiles, T, P, (unsigned*)ctx->d_ticket);   // T == 0: an empty shard
     ctx->launches++;
     if (T > 0) {
         const size_t smem = (size_t)256 * L.wb;

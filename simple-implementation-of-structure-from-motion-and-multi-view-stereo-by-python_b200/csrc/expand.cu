@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(256)
                  int32_t* __restrict__ counts /*[F]*/, const CamGeom* __restrict__ geom, int64_t* __restrict__ cand_slot,
                  int64_t* __restrict__ cand_parent, double* __restrict__ cand_c, double* __restrict__ cand_n,
                  int32_t* __restrict__ cand_ref, int32_t* __restrict__ cand_px, const int64_t* __restrict__ d_F = nullptr,
-                 int64_t F_clamp = 0) {
+                 int64_t F_clamp = 0, uint8_t* __restrict__ live_buf = nullptr, int live_pitch = 0) {
     const int lane = threadIdx.x & 31;
     const int64_t f = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     if (d_F) {
@@ -81,7 +81,10 @@ __global__ void __launch_bounds__(256)
         const int v = v0 + lane;
         const bool seen = ok && v < V && ((vis[v >> 6] >> (v & 63)) & 1ull);
         unsigned live = 0u;                                       // bit k: diagonal k of view v survives
-        if (seen) {
+        if (PASS == 2 && live_buf) {
+            // the count pass left the surviving diagonals of every (patch, view): no second probe of cells and claims
+            live = (v < V) ? live_buf[f * live_pitch + v] : 0u;
+        } else if (seen) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const int ti = ci + c_di[k], tj = cj + c_dj[k];
@@ -98,6 +101,7 @@ __global__ void __launch_bounds__(256)
             }
         }
         if (PASS == 0) continue;
+        if (PASS == 1 && live_buf && v < V) live_buf[f * live_pitch + v] = (uint8_t)live;
         const int n_live = __popc(live);
         int incl = n_live;
 #pragma unroll
@@ -491,6 +495,20 @@ int mvs_launch_publish(mvs_ctx* ctx, int64_t N, const uint64_t* vis, const doubl
 int mvs_launch_commit_wire(mvs_ctx* ctx, const void* inbox_local, int world, int64_t capacity, int parity, int64_t M,
                            void* next_frontier, int64_t* d_n_next, cudaStream_t s);
 
+// Everything the host needs to know about a round, written by ONE tiny kernel straight into pinned (device-mapped)
+// host memory: {accepted, candidates of the next round, kept per rank, barrier error flag}.  Replaces three small
+// device->host copies (and a fourth for the barrier flag), each of which cost a few microseconds of a ~160 us round.
+__global__ void __launch_bounds__(32) round_report(const int64_t* __restrict__ d_n_next, const int64_t* __restrict__ d_M_next,
+                                                   const uint8_t* __restrict__ inbox_half, int64_t region_bytes, int world,
+                                                   const int* __restrict__ barrier_err, volatile int64_t* __restrict__ host_out) {
+    const int t = threadIdx.x;
+    if (t == 0) host_out[0] = *d_n_next;
+    if (t == 1) host_out[1] = d_M_next ? *d_M_next : 0;
+    if (t >= 2 && t < 2 + world) host_out[t] = *reinterpret_cast<const int64_t*>(inbox_half + (int64_t)(t - 2) * region_bytes);
+    if (t == 2 + world) host_out[t] = barrier_err ? (int64_t)*barrier_err : 0;
+    __threadfence_system();
+}
+
 // grow a device buffer, KEEPING its first `keep` bytes
 static int ensure_keep(void** p, size_t* cap, size_t bytes, size_t keep, cudaStream_t s, const char* what) {
     if (bytes <= *cap && *p) return MVS_OK;
@@ -518,6 +536,7 @@ static int generate_count(mvs_ctx* ctx, const void* frontier, int64_t F_upper, c
     int rc;
     if ((rc = mvs_ensure((void**)&ctx->d_counts, &ctx->counts_bytes, sizeof(int32_t) * F_upper, "slot counts")) != MVS_OK) return rc;
     if ((rc = mvs_ensure((void**)&ctx->d_scan, &ctx->scan_bytes, sizeof(int64_t) * ((F_upper + 1023) / 1024 + 2), "scan")) != MVS_OK) return rc;
+    if ((rc = mvs_ensure((void**)&ctx->d_live, &ctx->live_bytes, (size_t)F_upper * ctx->V, "surviving slots")) != MVS_OK) return rc;
     ctx->epoch++;
     const int rb = rec_bytes_of(ctx);
     const unsigned blocks = (unsigned)((F_upper + 7) / 8);           // one warp per frontier patch
@@ -527,7 +546,7 @@ static int generate_count(mvs_ctx* ctx, const void* frontier, int64_t F_upper, c
                                           nullptr, nullptr, nullptr, d_F, F_clamp);
     expand_slots<1><<<blocks, 256, 0, s>>>((const uint8_t*)frontier, F_upper, rb, ctx->V, ctx->cell_size, ctx->wc, ctx->hc,
                                           ctx->d_cells, ctx->d_claim, ctx->epoch, ctx->d_counts, nullptr, nullptr, nullptr,
-                                          nullptr, nullptr, nullptr, nullptr, d_F, F_clamp);
+                                          nullptr, nullptr, nullptr, nullptr, d_F, F_clamp, ctx->d_live, ctx->V);
     ctx->launches += 2;
     MVS_CUDA_CHECK(cudaGetLastError());
     if ((rc = mvs_exclusive_scan_i32(ctx->d_counts, F_upper, ctx->d_scan, d_total, s)) != MVS_OK) return rc;
@@ -604,7 +623,8 @@ extern "C" int mvs_expand_run(mvs_ctx* ctx, const void* seeds, int64_t n_seeds, 
             expand_slots<2><<<(unsigned)((F + 7) / 8), 256, 0, s>>>(frontier, F, rb, ctx->V, ctx->cell_size, ctx->wc, ctx->hc,
                                                                         ctx->d_cells, ctx->d_claim, ctx->epoch, ctx->d_counts,
                                                                         ctx->d_geom, ctx->cand_slot, ctx->cand_parent, ctx->cand_c,
-                                                                        ctx->cand_n, ctx->cand_ref, ctx->cand_px);
+                                                                        ctx->cand_n, ctx->cand_ref, ctx->cand_px, nullptr, 0, ctx->d_live,
+                                                                        ctx->V);
             expand_geometry<<<(unsigned)((M + 127) / 128), 128, 0, s>>>(frontier, rb, ctx->V, ctx->cell_size, M, ctx->cand_slot,
                                                                        ctx->d_geom, ctx->cand_c, ctx->cand_n, ctx->cand_ref,
                                                                        ctx->cand_px, ctx->cand_gate, 0.05 / prm->scale);
@@ -634,27 +654,28 @@ extern "C" int mvs_expand_run(mvs_ctx* ctx, const void* seeds, int64_t n_seeds, 
             // ---- commit (identical on every GPU): next frontier appended to the output buffer
             uint8_t* next = ctx->d_out + T * rb;
             if ((rc = mvs_launch_commit_wire(ctx, inbox_local, world, shard_cap, parity, M, next, d_n_next, s)) != MVS_OK) return rc;
-            // kept-per-rank headers of this round (statistics)
-            MVS_CUDA_CHECK(cudaMemcpy2DAsync(&h_back[2], sizeof(int64_t),
-                                             (const uint8_t*)inbox_local + (size_t)parity * world * (mvs_exchange_bytes(ctx, world, shard_cap) / (2 * world)),
-                                             (size_t)(mvs_exchange_bytes(ctx, world, shard_cap) / (2 * world)), sizeof(int64_t), world,
-                                             cudaMemcpyDeviceToHost, s));
             // ---- speculative claim + count passes of the NEXT round on the device-side frontier size
             const int64_t remaining = max_iter - expanded;
+            const int64_t* d_M_next = nullptr;
             if (k + 1 < max_rounds && remaining > 0) {
                 F_next_upper = M;                              // accepted <= candidates
                 if ((rc = generate_count(ctx, next, F_next_upper, d_n_next, remaining, &d_total, s)) != MVS_OK) return rc;
-                MVS_CUDA_CHECK(cudaMemcpyAsync(&h_back[1], d_total, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-            } else {
-                h_back[1] = 0;
+                d_M_next = d_total;
             }
-            MVS_CUDA_CHECK(cudaMemcpyAsync(&h_back[0], d_n_next, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+            // ---- one read-back per round
+            const int64_t region_bytes = mvs_exchange_bytes(ctx, world, shard_cap) / (2 * world);
+            round_report<<<1, 32, 0, s>>>(d_n_next, d_M_next, (const uint8_t*)inbox_local + (size_t)parity * world * region_bytes,
+                                          region_bytes, world,
+                                          (world > 1 && ctx->d_barrier_state) ? (const int*)((const uint8_t*)ctx->d_barrier_state + 8) : nullptr,
+                                          h_back);
+            ctx->launches++;
+            MVS_CUDA_CHECK(cudaGetLastError());
             if (prm->timing) MVS_CUDA_CHECK(cudaEventRecord(ctx->ev_round[1], s));
             MVS_CUDA_CHECK(cudaStreamSynchronize(s));
             n_next = h_back[0];
             M_next = h_back[1];
             for (int r = 0; r < world; ++r) passed += h_back[2 + r];
-            if (world > 1 && mvs_p2p_barrier_failed(ctx, s)) {
+            if (world > 1 && h_back[2 + world] != 0) {
                 mvs_set_error("mvs_expand_run: a peer GPU did not reach the round barrier (round %lld)", (long long)k);
                 return MVS_ERR_STATE;
             }

@@ -273,7 +273,7 @@ extern "C" int mvs_destroy(mvs_ctx* ctx) {
                     ctx->cand_gate};
     for (void* b : bufs)
         if (b) cudaFree(b);
-    void* more2[] = {ctx->d_out, ctx->d_inbox, ctx->d_round_n, ctx->d_barrier_state};
+    void* more2[] = {ctx->d_out, ctx->d_inbox, ctx->d_round_n, ctx->d_barrier_state, ctx->d_ticket, ctx->d_live};
     for (void* b : more2)
         if (b) cudaFree(b);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);

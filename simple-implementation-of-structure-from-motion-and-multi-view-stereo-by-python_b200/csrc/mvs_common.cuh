@@ -124,7 +124,10 @@ struct mvs_ctx {
     size_t inbox_bytes;
     int64_t* d_round_n;
     size_t round_n_bytes;
-    void* d_barrier_state;            // {u64 epoch, int error}
+    void* d_barrier_state;            // {u64 reserved, int error}
+    void* d_ticket;                   // last-CTA ticket of publish_count_scan
+    uint8_t* d_live;                  // [F, V] surviving diagonals of every (frontier patch, view), count pass -> emit pass
+    size_t live_bytes;
     void* h_pinned;                   // small pinned read-back area
     cudaEvent_t ev_round[2];
 };
