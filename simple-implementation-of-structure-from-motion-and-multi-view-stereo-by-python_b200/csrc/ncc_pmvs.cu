@@ -93,12 +93,11 @@ __device__ __forceinline__ float warp_sum(float v) {
 //   u = uc + (a*gxu + b*gyu) / z,  gxu = hx.X - uc*hx.Z, ...,  z = Z0 + a*hxZ + b*hyZ
 // so fp32 only ever carries offsets of a few pixels (error ~1e-6 px instead of ~5e-5 px).
 // uc, vc are split into integer part and fraction.  Everything is stored divided by Z0 (z/Z0 = 1 + a*ex + b*ey),
-// which leaves TEN floats: every lane fetches them per view as two LDS.128 and one LDS.64 -- the shared-memory
-// wavefronts of these broadcasts are what binds the kernel (ncu: l1tex data pipe 84-89 %).
-struct __align__(16) ViewAffine {
+// which leaves TEN floats: every lane fetches them per view as two LDS.128 and one LDS.64.
+struct ViewAffine {
     float iu, fu, iv, fv;
     float ex, ey, gxu, gyu;      // ex = hxZ/Z0, ey = hyZ/Z0 (NaN when the centre is not in front of the view)
-    float gxv, gyv, pad0, pad1;
+    float gxv, gyv;
 };
 
 // Bilinear sample through the gather path.  (u0, v0) = integer tap origin (pixel centres at
@@ -118,8 +117,9 @@ __device__ __forceinline__ float tap4(const bool checked, cudaTextureObject_t te
     return fmaf(fv, bot - top, top);
 }
 
-template <int MU, bool REDUCE_A, int MINB, bool ONE_ATLAS>
+template <int MU, bool REDUCE_A, int MINB, bool ONE_ATLAS, int VB>
 __global__ void __launch_bounds__(32, MINB) ncc_score_pmvs(const PmvsArgs A, int64_t N) {
+    static_assert(VB == 16 || VB == 32, "views per reduction batch");
     constexpr int NS = MU * MU;
     constexpr int SPL = (NS + 31) / 32;                    // samples per lane
     constexpr float HALF = 0.5f * (MU - 1);
@@ -127,17 +127,24 @@ __global__ void __launch_bounds__(32, MINB) ncc_score_pmvs(const PmvsArgs A, int
     // kernel arguments only, i.e. is provably warp-uniform, which lets the texture handle travel
     // in a uniform register (no per-lane waterfall loop around TLD4) and keeps the gathers of a
     // batch of views in flight together.
-    __shared__ ViewAffine s_view[1][33];                   // 32 views of the current block + the reference view
+    // 32 views of the current block + the reference view; three arrays (not 48-byte records with 8 bytes of padding):
+    // the 264 bytes decide whether 31 or 32 warps fit an SM at mu = 7
+    __shared__ float4 s_va[33], s_vb[33];                  // iu fu iv fv | ex ey gxu gyu
+    __shared__ float2 s_vc[33];                            // gxv gyv
     // samples of 16 views.  Row stride = 2 (mod 32) and the second half-warp starts at an odd sample
     // offset, so the 32 lanes of phase 2 (16 views x 2 sample halves) hit 32 different banks.
-    constexpr int VSTRIDE = ((MU * MU + 29) / 32) * 32 + 2;
-    __shared__ float s_val[16][VSTRIDE];
-    __shared__ float s_dref[MU * MU];                      // pivot-shifted samples of the reference view
-    // Projection of the CURRENT centre through the first 64 views (uc, vc in fp64, depth), kept across consecutive
+    // Phase 2 reads a view's samples four at a time (VB = 32: every lane ONE view and all its samples; VB = 16: lane L
+    // and lane L + 16 share view L, the first and the second part of its sample quads); the row stride is a multiple of
+    // 4 floats with an odd quotient, so the eight lanes of a quarter-warp read eight different 16-byte bank groups.
+    constexpr int NS4 = (NS + 3) / 4;                      // sample quads per view
+    constexpr int VSTRIDE = 4 * (NS4 | 1);
+    __shared__ __align__(16) float s_val[VB][VSTRIDE];
+    __shared__ __align__(16) float s_dref[4 * NS4];        // pivot-shifted samples of the reference view
+    // Projection of the CURRENT centre through the first 64 views (floor and fraction of uc, vc; depth), kept across consecutive
     // hypotheses with the same centre and reference view -- the normals of one depth in a depth x normal set -- so
     // that the fp64 part of the staging (12 loads, 3 dot products, a division) runs once per centre, not per normal.
     // Lane l only ever reads back what it wrote itself (views l and 32 + l): no synchronisation.
-    __shared__ double s_cuc[64], s_cvc[64];
+    __shared__ float4 s_cuv[64];                           // floor(uc), uc - floor(uc), floor(vc), vc - floor(vc)
     __shared__ float s_czv[64];
 
     // ONE_ATLAS (every BASELINE shape up to 128 x 1080p): all views are tiles of one texture, so its handle is read
@@ -172,6 +179,7 @@ __global__ void __launch_bounds__(32, MINB) ncc_score_pmvs(const PmvsArgs A, int
         double pc0 = 0.0, pc1 = 0.0, pc2 = 0.0;            // centre / reference view whose projections are cached
         int pr = -1;
         unsigned cached = 0u;                              // bit b: the cache of view block b belongs to (pc, pr)
+        double px = 0.0, py = 0.0, pZc = 0.0;              // ... and its projection through the reference view
         for (int gi = 0; gi < group; ++gi) {
             const int64_t h = set * group + gi;
             if (h >= N) break;
@@ -182,10 +190,21 @@ __global__ void __launch_bounds__(32, MINB) ncc_score_pmvs(const PmvsArgs A, int
             bool hyp_ok = (r >= 0) && (r < A.V);
             float ex[3] = {0, 0, 0}, ey[3] = {0, 0, 0}, step = 0.0f;
             int row = 0, col = 0;
+            // consecutive hypotheses with the same centre and reference view (the normals of one depth): the fp64
+            // projections of the centre are taken over from the previous hypothesis
+            const bool same_centre = !reduce_a && r == pr && c0 == pc0 && c1 == pc1 && c2 == pc2;
+            if (!same_centre) {
+                cached = 0u;
+                pc0 = c0; pc1 = c1; pc2 = c2; pr = r;
+            }
             if (hyp_ok) {
                 const CamProj& cr = A.cams[r];
-                project_ref(cr, c0, c1, c2, x, y);
-                const double Zc = cr.r[6] * c0 + cr.r[7] * c1 + cr.r[8] * c2 + cr.t[2];
+                if (!same_centre) {
+                    project_ref(cr, c0, c1, c2, px, py);
+                    pZc = cr.r[6] * c0 + cr.r[7] * c1 + cr.r[8] * c2 + cr.t[2];
+                }
+                x = px; y = py;
+                const double Zc = pZc;
                 if (reduce_a) {
                     hyp_ok = window_anchor(x, y, A.H, A.W, (MU - 1) / 2, row, col);
                 } else {
@@ -220,35 +239,34 @@ __global__ void __launch_bounds__(32, MINB) ncc_score_pmvs(const PmvsArgs A, int
                 const double* c64 = A.cam64 + cam;
                 const float* c32 = A.cam32 + cam;
                 const int Vs = A.cam_stride;
-                const double cvcx = c64[14 * Vs], cvcy = c64[15 * Vs];
-                double uc, vc;
+                float4 cuv;                                 // the centre's projection, split: integer part and fraction
                 float Zvf;
                 if (use_cache) {
-                    uc = s_cuc[cidx];
-                    vc = s_cvc[cidx];
+                    cuv = s_cuv[cidx];
                     Zvf = s_czv[cidx];
                 } else {
+                    const double cvcx = c64[14 * Vs], cvcy = c64[15 * Vs];
                     const double cvfx = c64[12 * Vs], cvfy = c64[13 * Vs];
                     const double Xc = c64[0] * c0 + c64[1 * Vs] * c1 + c64[2 * Vs] * c2 + c64[9 * Vs];
                     const double Yc = c64[3 * Vs] * c0 + c64[4 * Vs] * c1 + c64[5 * Vs] * c2 + c64[10 * Vs];
                     const double Zv = c64[6 * Vs] * c0 + c64[7 * Vs] * c1 + c64[8 * Vs] * c2 + c64[11 * Vs];
                     const double izd = 1.0 / Zv;
-                    uc = (cvfx * Xc + cvcx * Zv) * izd;
-                    vc = (cvfy * Yc + cvcy * Zv) * izd;
+                    const double uc = (cvfx * Xc + cvcx * Zv) * izd;
+                    const double vc = (cvfy * Yc + cvcy * Zv) * izd;
+                    const double ucf = floor(uc), vcf = floor(vc);
+                    cuv = make_float4((float)ucf, (float)(uc - ucf), (float)vcf, (float)(vc - vcf));
                     Zvf = (float)Zv;
                     if (cidx >= 0) {
-                        s_cuc[cidx] = uc;
-                        s_cvc[cidx] = vc;
+                        s_cuv[cidx] = cuv;
                         s_czv[cidx] = Zvf;
                     }
                 }
                 ViewAffine va;
-                const double ucf = floor(uc), vcf = floor(vc);
                 // integer parts carry the view's tile origin inside the atlas and the +1 that addresses the
                 // centre of the 2x2 gather footprint, so a tap coordinate is iu + floor(.) with no further adds
                 const float2 org = A.off[v];
-                va.iu = (float)ucf + org.x + 1.0f; va.fu = (float)(uc - ucf);
-                va.iv = (float)vcf + org.y + 1.0f; va.fv = (float)(vc - vcf);
+                va.iu = cuv.x + org.x + 1.0f; va.fu = cuv.y;
+                va.iv = cuv.z + org.y + 1.0f; va.fv = cuv.w;
                 const float Z0 = Zvf;
                 const float iZ0 = Z0 > 0.0f ? rcp_approx(Z0) : nanf("");   // behind the camera: every tap test fails on NaN
                 const float f0 = c32[0], f1 = c32[1 * Vs], f2 = c32[2 * Vs], f3 = c32[3 * Vs], f4 = c32[4 * Vs], f5 = c32[5 * Vs],
@@ -260,15 +278,17 @@ __global__ void __launch_bounds__(32, MINB) ncc_score_pmvs(const PmvsArgs A, int
                 const float ry1 = f3 * ey[0] + f4 * ey[1] + f5 * ey[2];
                 const float ry2 = f6 * ey[0] + f7 * ey[1] + f8 * ey[2];
                 // hx.X - uc*hx.Z = step*(fx*rx0 + (cx - uc)*rx2): the principal point cancels against uc
-                const float du = (float)(cvcx - uc), dv = (float)(cvcy - vc);
+                // (fp32 is enough here: du, dv only multiply the perspective terms rx2, ry2 ~ 1e-3 of the others)
+                const float du = (c32[11 * Vs] - cuv.x) - cuv.y, dv = (c32[12 * Vs] - cuv.z) - cuv.w;
                 const float hxZ = step * rx2, hyZ = step * ry2;
                 const float gxu = step * fmaf(du, rx2, cffx * rx0), gyu = step * fmaf(du, ry2, cffx * ry0);
                 const float gxv = step * fmaf(dv, rx2, cffy * rx1), gyv = step * fmaf(dv, ry2, cffy * ry1);
                 va.ex = hxZ * iZ0; va.ey = hyZ * iZ0;
                 va.gxu = gxu * iZ0; va.gyu = gyu * iZ0;
                 va.gxv = gxv * iZ0; va.gyv = gyv * iZ0;
-                va.pad0 = va.pad1 = 0.0f;
-                s_view[wib][slot] = va;
+                s_va[slot] = make_float4(va.iu, va.fu, va.iv, va.fv);
+                s_vb[slot] = make_float4(va.ex, va.ey, va.gxu, va.gyu);
+                s_vc[slot] = make_float2(va.gxv, va.gyv);
                 // "safe" view: the whole mu x mu footprint provably stays inside the image and in front of
                 // the camera (bound on the tap offsets from the staged increments, 0.01 px of slack), so its
                 // taps need no per-tap bounds test
@@ -276,7 +296,7 @@ __global__ void __launch_bounds__(32, MINB) ncc_score_pmvs(const PmvsArgs A, int
                 const float izm = rcp_approx(zmin);            // (an IEEE division's slow path would break the warp-uniformity proof below)
                 const float ru = HALF * (fabsf(gxu) + fabsf(gyu)) * izm + 0.01f;
                 const float rv = HALF * (fabsf(gxv) + fabsf(gyv)) * izm + 0.01f;
-                const float ucl = (float)uc, vcl = (float)vc;
+                const float ucl = cuv.x + cuv.y, vcl = cuv.z + cuv.w;
                 return !reduce_a && (zmin > 0.0f) && (ucl - ru >= 0.0f) && (ucl + ru <= wm2 + 0.98f) && (vcl - rv >= 0.0f) &&
                        (vcl + rv <= hm2 + 0.98f);
             };
@@ -284,9 +304,8 @@ __global__ void __launch_bounds__(32, MINB) ncc_score_pmvs(const PmvsArgs A, int
             // Issue the taps of the view staged in `slot` (no warp-synchronous operation in here,
             // so the gathers of a whole batch of views are in flight together).
             auto issue_view = [&](const bool checked, int slot, cudaTextureObject_t tex, float2 off, float (&val)[SPL], bool& ok_all) {
-                const float4* pv = reinterpret_cast<const float4*>(&s_view[wib][slot]);
-                const float4 q0 = pv[0], q1 = pv[1];                      // iu fu iv fv | ex ey gxu gyu
-                const float2 q2 = *reinterpret_cast<const float2*>(pv + 2);  // gxv gyv
+                const float4 q0 = s_va[slot], q1 = s_vb[slot];            // iu fu iv fv | ex ey gxu gyu
+                const float2 q2 = s_vc[slot];                             // gxv gyv
                 ok_all = true;
 #pragma unroll
                 for (int q = 0; q < SPL; ++q) {
@@ -325,13 +344,9 @@ __global__ void __launch_bounds__(32, MINB) ncc_score_pmvs(const PmvsArgs A, int
                 if (hyp_ok) {                              // uniform across the warp
                     // ---- stage this block's 32 views (one lane each); block 0 also stages the reference view
                     __syncwarp();
-                    const bool same_c = !reduce_a && w32 < 2 && ((cached >> w32) & 1u) && r == pr && c0 == pc0 && c1 == pc1 && c2 == pc2;
+                    const bool same_c = !reduce_a && w32 < 2 && ((cached >> w32) & 1u);
                     const bool safe = stage_view(min(w32 * 32 + lane, A.V - 1), lane, w32 < 2 ? w32 * 32 + lane : -1, same_c);   // lanes past the last view shadow it
-                    if (w32 < 2 && !same_c) {              // (uniform) this block's cache now belongs to the current centre
-                        if (!(r == pr && c0 == pc0 && c1 == pc1 && c2 == pc2)) cached = 0u;
-                        pc0 = c0; pc1 = c1; pc2 = c2; pr = r;
-                        cached |= 1u << w32;
-                    }
+                    if (w32 < 2) cached |= 1u << w32;      // (uniform) this block's cache now belongs to the current centre
                     // one vote per half: every view of the half safe -> its taps skip the bounds tests
                     safe_lo = __all_sync(FULL, safe || lane >= 16);
                     safe_hi = __all_sync(FULL, safe || lane < 16);
@@ -360,16 +375,21 @@ __global__ void __launch_bounds__(32, MINB) ncc_score_pmvs(const PmvsArgs A, int
                     const uint32_t cand32 =
                         A.cand ? (uint32_t)(__ldg(A.cand + h * mw + (w32 >> 1)) >> (32 * (w32 & 1))) : 0xffffffffu;
 #pragma unroll 1
-                    for (int half = 0; half < 2; ++half) {
+                    for (int bt = 0; bt < 32 / VB; ++bt) {                   // reduction batches of VB views
+                        if (w32 * 32 + bt * VB >= A.V) break;
+                        constexpr int TB = SPL == 1 ? 16 : (SPL == 2 ? 8 : 4);
+                        uint32_t bad = 0u;                                   // bit j: some tap of view j of the batch is outside
+                        __syncwarp();                                        // the previous batch's readers are done
+#pragma unroll 1
+                        for (int hh = 0; hh < VB / 16; ++hh) {
+                        const int half = bt * (VB / 16) + hh;                // which 16 views of the block of 32
                         const int vbase = w32 * 32 + half * 16;
                         if (vbase >= A.V) break;
                         // ---- phase 1: lanes span the samples.  Taps of TB views are issued together, the
                         // interpolated values go to shared memory [view][sample].
-                        constexpr int TB = SPL == 1 ? 16 : (SPL == 2 ? 8 : 4);
-                        uint32_t bad = 0u;                                   // bit j: some tap of view j is outside
-                        __syncwarp();                                        // the previous half's readers are done
                         if (half ? safe_hi : safe_lo) {                      // safe half: taps without bounds tests
-#pragma unroll
+#pragma unroll 1                                             // (unrolled, the mu = 7 loop body outgrows the instruction cache:
+                                                             //  ncu "no instruction" stall 2.0 per issue)
                         for (int j0 = 0; j0 < 16; j0 += TB) {
                             float val[TB][SPL];
                             bool okl[TB];
@@ -380,14 +400,15 @@ __global__ void __launch_bounds__(32, MINB) ncc_score_pmvs(const PmvsArgs A, int
                                            make_float2(0.0f, 0.0f), val[jj], okl[jj]);      // the tile origin only enters the bounds tests
 #pragma unroll
                             for (int jj = 0; jj < TB; ++jj) {
-                                if (!okl[jj]) bad |= 1u << (j0 + jj);
+                                if (!okl[jj]) bad |= 1u << (hh * 16 + j0 + jj);
 #pragma unroll
                                 for (int q = 0; q < SPL; ++q)
-                                    if (live[q]) s_val[j0 + jj][lane + 32 * q] = val[jj][q];
+                                    if (live[q]) s_val[hh * 16 + j0 + jj][lane + 32 * q] = val[jj][q];
                             }
                         }
                         } else {
-#pragma unroll
+#pragma unroll 1                                             // (unrolled, the mu = 7 loop body outgrows the instruction cache:
+                                                             //  ncu "no instruction" stall 2.0 per issue)
                         for (int j0 = 0; j0 < 16; j0 += TB) {
                             float val[TB][SPL];
                             bool okl[TB];
@@ -398,33 +419,76 @@ __global__ void __launch_bounds__(32, MINB) ncc_score_pmvs(const PmvsArgs A, int
                                            c_off[min(vbase + j0 + jj, A.V - 1)], val[jj], okl[jj]);
 #pragma unroll
                             for (int jj = 0; jj < TB; ++jj) {
-                                if (!okl[jj]) bad |= 1u << (j0 + jj);
+                                if (!okl[jj]) bad |= 1u << (hh * 16 + j0 + jj);
 #pragma unroll
                                 for (int q = 0; q < SPL; ++q)
-                                    if (live[q]) s_val[j0 + jj][lane + 32 * q] = val[jj][q];
+                                    if (live[q]) s_val[hh * 16 + j0 + jj][lane + 32 * q] = val[jj][q];
                             }
                         }
                         }
-                        const uint32_t usable16 = ~__reduce_or_sync(FULL, bad);
+                        }
+                        const uint32_t usable = ~__reduce_or_sync(FULL, bad);
                         __syncwarp();
-                        // ---- phase 2: lanes span the VIEWS.  Lane L sums half of the samples of view L & 15
-                        // (pivot = the view's first sample, so low-variance windows keep full fp32 precision);
-                        // one shuffle per quantity joins the halves -- no butterfly.
-                        constexpr int NH = (NS + 1) / 2;
+                        if (VB == 32) {
+                            // ---- phase 2: lane L owns view L of the block and sums all its samples, four per load
+                            // (pivot = the view's first sample, so low-variance windows keep full fp32 precision)
+                            const float4* rowq = reinterpret_cast<const float4*>(s_val[lane]);
+                            const float4* refq = reinterpret_cast<const float4*>(s_dref);
+                            float pivot = 0.0f, Sd = 0.0f, SSd = 0.0f, SAB = 0.0f;
+#pragma unroll
+                            for (int g = 0; g < NS4; ++g) {
+                                const float4 xq = rowq[g], dq = refq[g];
+                                const float xs[4] = {xq.x, xq.y, xq.z, xq.w}, ds[4] = {dq.x, dq.y, dq.z, dq.w};
+                                if (g == 0) pivot = xq.x;
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    if (4 * g + e < NS && 4 * g + e > 0) {   // (the pivot's own deviation is 0)
+                                        const float dd = xs[e] - pivot;
+                                        Sd += dd;
+                                        SSd = fmaf(dd, dd, SSd);
+                                        SAB = fmaf(dd, ds[e], SAB);
+                                    }
+                                }
+                            }
+                            const int v = w32 * 32 + lane;
+                            const float ss = SSd - Sd * Sd * (1.0f / NS);
+                            const float cov = SAB - Sd * Sr * (1.0f / NS);
+                            const bool scored = (v < A.V) && (v != r) && ((usable >> lane) & 1u) && ((cand32 >> lane) & 1u) &&
+                                                (ss * (1.0f / NS) >= PMVS_VAR_MIN) && (ssr * (1.0f / NS) >= PMVS_VAR_MIN);
+                            const float val_ncc = cov * rsqrtf(ss * ssr) * cn;
+                            const bool vis = scored && (val_ncc > A.thr);
+                            if (vis) acc += (double)val_ncc;
+                            word = __ballot_sync(FULL, vis);
+                            if (A.ncc_out && v < A.V) A.ncc_out[h * A.V + v] = scored ? val_ncc : nanf("");
+                        } else {
+                        // ---- phase 2: lanes span the VIEWS.  Lanes L and L + 16 sum the first Q0 and the remaining
+                        // sample quads of view L (pivot = the view's first sample, so low-variance windows keep full
+                        // fp32 precision); one shuffle per quantity joins the two parts -- no butterfly.
+                        const int half = bt, vbase = w32 * 32 + half * 16;
                         const int vj = lane & 15;
-                        const float* row = s_val[vj];
-                        const float pivot = row[0];
-                        const int m0 = (lane & 16) ? NH : 0;
-                        const int m1 = (lane & 16) ? NS : NH;
+                        constexpr int Q0 = (NS4 + 1) / 2;                    // quads of the first part (all complete)
+                        constexpr int R1 = NS - 4 * Q0;                      // samples of the second part
+                        const bool lo = lane < 16;
+                        const float pivot = s_val[vj][0];
+                        const float4* rowq = reinterpret_cast<const float4*>(s_val[vj]) + (lo ? 0 : Q0);
+                        const float4* refq = reinterpret_cast<const float4*>(s_dref) + (lo ? 0 : Q0);
                         float Sd = 0.0f, SSd = 0.0f, SAB = 0.0f;
 #pragma unroll
-                        for (int t = 0; t < NH; ++t) {
-                            const int m = m0 + t;
-                            if (m < m1) {
-                                const float dd = row[m] - pivot;
-                                Sd += dd;
-                                SSd = fmaf(dd, dd, SSd);
-                                SAB = fmaf(dd, s_dref[m], SAB);
+                        for (int g = 0; g < Q0; ++g) {
+                            float4 xq = make_float4(0.f, 0.f, 0.f, 0.f), dq = xq;
+                            if (4 * g < R1 || lo) {                          // (quads past the second part's end are not read)
+                                xq = rowq[g];
+                                dq = refq[g];
+                            }
+                            const float xs[4] = {xq.x, xq.y, xq.z, xq.w}, ds[4] = {dq.x, dq.y, dq.z, dq.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                if (4 * g + e < R1 || lo) {                  // compile-time true for the samples both parts have
+                                    const float dd = xs[e] - pivot;
+                                    Sd += dd;
+                                    SSd = fmaf(dd, dd, SSd);
+                                    SAB = fmaf(dd, ds[e], SAB);
+                                }
                             }
                         }
                         Sd += __shfl_xor_sync(FULL, Sd, 16);
@@ -433,7 +497,7 @@ __global__ void __launch_bounds__(32, MINB) ncc_score_pmvs(const PmvsArgs A, int
                         const int v = vbase + vj;
                         const float ss = SSd - Sd * Sd * (1.0f / NS);
                         const float cov = SAB - Sd * Sr * (1.0f / NS);
-                        const bool scored = (v < A.V) && (v != r) && ((usable16 >> vj) & 1u) &&
+                        const bool scored = (v < A.V) && (v != r) && ((usable >> vj) & 1u) &&
                                             ((cand32 >> (half * 16 + vj)) & 1u) && (ss * (1.0f / NS) >= PMVS_VAR_MIN) &&
                                             (ssr * (1.0f / NS) >= PMVS_VAR_MIN);
                         const float val_ncc = cov * rsqrtf(ss * ssr) * cn;
@@ -441,6 +505,7 @@ __global__ void __launch_bounds__(32, MINB) ncc_score_pmvs(const PmvsArgs A, int
                         if (vis) acc += (double)val_ncc;
                         word |= __ballot_sync(FULL, vis) << (half * 16);
                         if (A.ncc_out && v < A.V && lane < 16) A.ncc_out[h * A.V + v] = scored ? val_ncc : nanf("");
+                        }
                     }
                 } else if (A.ncc_out) {
                     for (int v = w32 * 32 + lane; v < min(A.V, w32 * 32 + 32); v += 32) A.ncc_out[h * A.V + v] = nanf("");
@@ -716,23 +781,46 @@ int mvs_launch_score_pmvs(mvs_ctx* ctx, int64_t N, const double* c, const double
         minb = e ? atoi(e) : 32;                           // 32 one-warp CTAs per SM (64 registers) measured best
     }
     const bool one = ctx->pmvs_n_atlas == 1;
+    // views per reduction batch: 32 up to mu = 5 (3.44 vs 3.66 ms per 2^20 hypotheses at mu = 5), 16 from mu = 7 on, where the
+    // 32-row sample buffer costs a quarter of the resident warps (6.25 vs 5.99 ms).  MVS_K2_VB overrides (tuning knob).
+    static int vb_env = -1;
+    if (vb_env < 0) {
+        const char* e = getenv("MVS_K2_VB");
+        vb_env = e ? atoi(e) : 0;
+    }
+    const int vb = vb_env == 16 || vb_env == 32 ? vb_env : (mu <= 5 ? 32 : 16);
+#define PMVS_GO(MU_, RA_, MB_, OA_, VB_)                                                                       \
+    do {                                                                                                   \
+        static bool carve = false;                         /* shared memory of 32 one-warp CTAs needs the largest carve-out */ \
+        if (!carve) {                                                                                      \
+            cudaFuncSetAttribute(ncc_score_pmvs<MU_, RA_, MB_, OA_, VB_>, cudaFuncAttributePreferredSharedMemoryCarveout, \
+                                 cudaSharedmemCarveoutMaxShared);                                          \
+            carve = true;                                                                                  \
+        }                                                                                                  \
+        ncc_score_pmvs<MU_, RA_, MB_, OA_, VB_><<<(int)blocks, 32, 0, s>>>(A, N);                          \
+    } while (0)
 #define PMVS_LAUNCH(MU_)                                                                                   \
     case MU_:                                                                                              \
         if (flags & MVS_PMVS_REDUCE_TO_REFEXACT)                                                           \
-            ncc_score_pmvs<MU_, true, 16, false><<<(int)blocks, 32, 0, s>>>(A, N);                         \
+            PMVS_GO(MU_, true, 16, false, 16);                                                             \
         else if (minb == 16)                                                                               \
-            ncc_score_pmvs<MU_, false, 16, false><<<(int)blocks, 32, 0, s>>>(A, N);                        \
+            PMVS_GO(MU_, false, 16, false, 16);                                                            \
         else if (minb == 24)                                                                               \
-            ncc_score_pmvs<MU_, false, 24, false><<<(int)blocks, 32, 0, s>>>(A, N);                        \
+            PMVS_GO(MU_, false, 24, false, 16);                                                            \
+        else if (one && vb == 32)                                                                          \
+            PMVS_GO(MU_, false, 32, true, 32);                                                             \
         else if (one)                                                                                      \
-            ncc_score_pmvs<MU_, false, 32, true><<<(int)blocks, 32, 0, s>>>(A, N);                         \
+            PMVS_GO(MU_, false, 32, true, 16);                                                             \
+        else if (vb == 32)                                                                                 \
+            PMVS_GO(MU_, false, 32, false, 32);                                                            \
         else                                                                                               \
-            ncc_score_pmvs<MU_, false, 32, false><<<(int)blocks, 32, 0, s>>>(A, N);                        \
+            PMVS_GO(MU_, false, 32, false, 16);                                                            \
         break;
     switch (mu) {
         PMVS_LAUNCH(3) PMVS_LAUNCH(5) PMVS_LAUNCH(7) PMVS_LAUNCH(9) PMVS_LAUNCH(11)
         default: mvs_set_error("Mode B grid size mu = %d not supported (3, 5, 7, 9, 11)", mu); return MVS_ERR_ARG;
     }
+#undef PMVS_GO
 #undef PMVS_LAUNCH
     if (ctx->profile) {
         MVS_CUDA_CHECK(cudaEventRecord(ctx->prof_ev[2 * pslot + 1], s));
