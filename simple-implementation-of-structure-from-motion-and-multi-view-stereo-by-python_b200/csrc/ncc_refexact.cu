@@ -252,7 +252,7 @@ struct ScoreArgs {
 // i.e. the same (row, (col - WID) >> 2): they read exactly the same 16-byte quads of every
 // view, so each quad is loaded ONCE and multiplied against NB reference windows.  GS is the
 // compile-time byte stride between pixel groups (4*Vp) or 0 = read it from the arguments.
-template <int WID, int LPH, int NB, int GS, bool WANT_NCC>
+template <int WID, int LPH, int NB, int GS, bool WANT_NCC, int UNR = 0>
 __device__ __forceinline__ void score_block(const ScoreArgs& A, const uint32_t (&anchor)[NB], const int64_t (&h)[NB],
                                             uint32_t (*sref)[2 * WID + 1][(2 * WID + 7) / 4], int lih, uint32_t hmask) {
     constexpr int K = 2 * WID + 1;
@@ -335,7 +335,9 @@ __device__ __forceinline__ void score_block(const ScoreArgs& A, const uint32_t (
 #pragma unroll
             for (int k = 0; k < 4; ++k) SAB[b][k] = 0;
         const uint8_t* prow = base + (int64_t)qc * 16;
-#pragma unroll
+        // UNR window rows per loop body (0 = all K): the fully unrolled pair + single instances of the 32-lane variants
+        // are 730 + 501 instructions and miss the instruction cache (ncu "no instruction" stall 2.4 per issue at 128 views)
+#pragma unroll(UNR ? UNR : K)
         for (int rr = 0; rr < K; ++rr) {
             uint32_t rw[NB][NG];
 #pragma unroll
@@ -448,7 +450,7 @@ __device__ __forceinline__ void score_block(const ScoreArgs& A, const uint32_t (
 // (MVS_ANCHOR_INVALID: rejected, result already written by bin_project); order[i] =
 // hypothesis index (NULL: identity) -- packed as entries[i] = (index, anchor) for ordered batches.
 // ---------------------------------------------------------------------------------
-template <int WID, int LPH, int GS, int MINB, bool WANT_NCC>
+template <int WID, int LPH, int GS, int MINB, bool WANT_NCC, int UNR = 0>
 __global__ void __launch_bounds__(256, MINB)
     ncc_score_gather(const ScoreArgs A, int64_t N, const uint32_t* __restrict__ anchors, const uint2* __restrict__ entries) {
     constexpr int K = 2 * WID + 1;
@@ -490,7 +492,7 @@ __global__ void __launch_bounds__(256, MINB)
             if (same) {
                 const uint32_t aa[2] = {a0, a1};
                 const int64_t hh[2] = {h0, h1};
-                score_block<WID, LPH, 2, GS, WANT_NCC>(A, aa, hh, sref, lih, hmask);
+                score_block<WID, LPH, 2, GS, WANT_NCC, UNR>(A, aa, hh, sref, lih, hmask);
             } else {
                 const uint32_t a2[2] = {a0, a1};
                 const int64_t h2[2] = {h0, h1};
@@ -499,7 +501,7 @@ __global__ void __launch_bounds__(256, MINB)
                     if (a2[t] == MVS_ANCHOR_INVALID) continue;
                     const uint32_t aa[1] = {a2[t]};
                     const int64_t hh[1] = {h2[t]};
-                    score_block<WID, LPH, 1, GS, WANT_NCC>(A, aa, hh, sref, lih, hmask);
+                    score_block<WID, LPH, 1, GS, WANT_NCC, UNR>(A, aa, hh, sref, lih, hmask);
                 }
             }
         }
@@ -1017,11 +1019,11 @@ static int k1_legacy() {
 #define MVS_K1_MINB 4
 #endif
 
-template <int WID, int LPH, int GS, int MINB = MVS_K1_MINB>
+template <int WID, int LPH, int GS, int MINB = MVS_K1_MINB, int UNR = 0>
 static int launch_gather_gs(mvs_ctx* ctx, const ScoreArgs& A, int64_t N, const uint32_t* anchors, const uint2* entries,
                             cudaStream_t s) {
     // the per-view NCC dump is a parity/debug output: its stores are compiled out of the hot variant
-    auto kern = A.ncc_out ? ncc_score_gather<WID, LPH, GS, MINB, true> : ncc_score_gather<WID, LPH, GS, MINB, false>;
+    auto kern = A.ncc_out ? ncc_score_gather<WID, LPH, GS, MINB, true, UNR> : ncc_score_gather<WID, LPH, GS, MINB, false, UNR>;
     const int64_t chunk = 8 * (32 / LPH) * 2 * MVS_K1_ITERS;
     const int64_t want = (N + chunk - 1) / chunk;
     const int64_t cap = (int64_t)ctx->sm_count * MINB * 8;
@@ -1076,13 +1078,26 @@ static int launch_gather(mvs_ctx* ctx, const ScoreArgs& A, int64_t N, const uint
     }
     if (WID == 5 && (Q == 32 || Q == 64)) {
         const int mb = k1_minb_override();                 // MVS_K1_MINB: resident CTAs per SM (tuning knob)
+        // MVS_K1_UNR: window rows per loop body of the 128-view variant (tuning knob).  Measured per 2^20 hypotheses on
+        // ring128_1080p: all 11 rows unrolled 1.075 ms, 1 row 1.034, 2 rows 1.012-1.016, 3 rows 1.015, 4 rows 1.048, 6 rows
+        // 1.100 -- the unrolled pair + single instances miss the instruction cache; ring256_4k (HBM-resident stack, two
+        // passes of 32 quads) wants the loads of all rows in flight instead: 2.00 ms unrolled, 2.15-2.19 with 2, 4 or 6 rows.
+        static int unr = -2;
+        if (unr == -2) {
+            const char* e = getenv("MVS_K1_UNR");
+            unr = e ? atoi(e) : -1;
+        }
         if (Q == 32) {
             if (mb == 2) return launch_gather_gs<5, 32, 512, 2>(ctx, A, N, anchors, entries, s);
             if (mb == 3) return launch_gather_gs<5, 32, 512, 3>(ctx, A, N, anchors, entries, s);
-            return launch_gather_gs<5, 32, 512>(ctx, A, N, anchors, entries, s);
+            if (unr == 0) return launch_gather_gs<5, 32, 512>(ctx, A, N, anchors, entries, s);
+            if (unr == 1) return launch_gather_gs<5, 32, 512, MVS_K1_MINB, 1>(ctx, A, N, anchors, entries, s);
+            if (unr == 3) return launch_gather_gs<5, 32, 512, MVS_K1_MINB, 3>(ctx, A, N, anchors, entries, s);
+            return launch_gather_gs<5, 32, 512, MVS_K1_MINB, 2>(ctx, A, N, anchors, entries, s);
         }
         if (mb == 2) return launch_gather_gs<5, 32, 1024, 2>(ctx, A, N, anchors, entries, s);
         if (mb == 3) return launch_gather_gs<5, 32, 1024, 3>(ctx, A, N, anchors, entries, s);
+        if (unr == 2) return launch_gather_gs<5, 32, 1024, MVS_K1_MINB, 2>(ctx, A, N, anchors, entries, s);
         return launch_gather_gs<5, 32, 1024>(ctx, A, N, anchors, entries, s);
     }
     return launch_gather_gs<WID, 32, 0>(ctx, A, N, anchors, entries, s);

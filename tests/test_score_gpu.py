@@ -121,7 +121,9 @@ def test_large_ring_other_windows(built_lib, V, wid, N):
 @pytest.mark.parametrize("V,H,W,N", [(48, 480, 640, 6000), (70, 120, 200, 6000), (33, 97, 131, 6000), (130, 120, 160, 6000),
                                      (7, 120, 160, 6000), (260, 120, 160, 6000),
                                      # >= 8192 hypotheses: the tile-ordered path with shared loads for neighbours
-                                     (33, 97, 131, 9000), (130, 120, 160, 9000), (7, 120, 160, 9000), (70, 120, 200, 20000)])
+                                     (33, 97, 131, 9000), (130, 120, 160, 9000), (7, 120, 160, 9000), (70, 120, 200, 20000),
+                                     # exactly 128 / 256 views: the specialised 32-lane variants of ring128_1080p / ring256_4k
+                                     (128, 120, 160, 9000), (256, 96, 128, 9000), (126, 120, 160, 5000)])
 def test_synthetic_ring_against_oracle(built_lib, V, H, W, N):
     """48-view 640x480 is the shape the headline metric is quoted on; 70 views needs two
     mask words; 33 x 97 x 131 has a view count and a width that are not multiples of 4; 130 and 260
