@@ -32,6 +32,7 @@ if ROOT not in sys.path:
 
 THR = 0.7
 BOUND = 3
+XPARTS_DEFAULT = 1        # position ranges of the overlapped exchange at N > 1 (mvs_exchange_set_parts); see profiles/README.md
 METRIC = "ncc_patch_hypotheses_per_sec"
 UNIT = "hyp/s"
 
@@ -352,7 +353,13 @@ def run_b200(args):
 
     exchange = "none"
     xchg = None
+    # overlap of the exchange with the scoring (mvs_exchange_set_parts): one K1 launch + publish per position range of
+    # the tile-ordered batch on streams of descending priority, the NVLink stores of a range under the scoring of the rest.
+    # Off on one GPU (nothing to hide); BENCH_XPARTS overrides.
+    xparts = int(os.environ.get("BENCH_XPARTS", str(XPARTS_DEFAULT if world > 1 else 1)))
     if not mode_b:
+        if lib.mvs_exchange_set_parts(ctx._h, xparts, 1 << 16) != 0:
+            raise RuntimeError(lib.mvs_last_error().decode())
         nbytes = int(lib.mvs_exchange_bytes(ctx._h, world, n))
         if world > 1:
             import torch.distributed._symmetric_memory as symm_mem
@@ -381,9 +388,8 @@ def run_b200(args):
                 dist.all_gather_into_tensor(g_idx, out["best_idx"])
                 dist.all_gather_into_tensor(g_avg, out["best_avg"])
             return
-        ctx.score_device(d_c, d_ref, min_ncc=THR, wid=w["wid"], out=out, stream=st.cuda_stream)
-        rc = lib.mvs_publish_accepted(ctx._h, n, p(out["vis_mask"]), p(out["avg"]), p(out["count"]), None, BOUND,
-                                      xchg["inbox_tab"], rank, world, n, parity, sp_)
+        rc = lib.mvs_score_publish(ctx._h, n, p(d_c), p(d_ref), THR, w["wid"], p(out["vis_mask"]), p(out["avg"]), p(out["count"]),
+                                   p(out["xy"]), None, BOUND, xchg["inbox_tab"], rank, world, n, parity, sp_)
         if rc == 0 and world > 1:
             rc = lib.mvs_p2p_barrier(ctx._h, xchg["flag_tab"], rank, world, sp_)
         if rc != 0:
@@ -444,8 +450,8 @@ def run_b200(args):
         ends[i].record(stream)
     barrier()
     clocks = sampler.stop()
-    if not mode_b and world > 1 and lib.mvs_p2p_barrier_failed(ctx._h, C.c_void_p(stream.cuda_stream)):
-        raise RuntimeError("a device-side barrier timed out waiting for a peer GPU")
+    if not mode_b and lib.mvs_p2p_barrier_failed(ctx._h, C.c_void_p(stream.cuda_stream)):
+        raise RuntimeError("a device-side barrier (waiting for a peer GPU) timed out")
     # the scoring kernel alone and the launch count: the same steps again, eagerly, with the library's
     # CUDA events around K1 on its launch stream (not part of the timed region above)
     prof_steps = min(args.steps, 20)
@@ -485,22 +491,30 @@ def run_b200(args):
     if mode_b:
         kept = int((out["best_idx"] >= 0).sum().item())
     else:
+        from mvs_b200 import records as _records
         half = xchg["inbox"][last_parity * world * region_bytes:(last_parity + 1) * world * region_bytes]
-        nw = (n + 31) // 32
-        ent_off = (16 + 8 * nw + 255) // 256 * 256
-        wb = 8 + 8 * mw
 
         def region_sum(r):
-            reg = half[r * region_bytes:(r + 1) * region_bytes]
-            k = int(reg[:8].view(torch.int64).item())
-            body = reg[: 16 + 8 * nw].view(torch.int64).sum() + reg[ent_off: ent_off + k * wb].view(torch.int64).sum()
-            return body.reshape(1), k
-        mine, kept = region_sum(rank)
-        want_kept = int(((out["count"] >= BOUND)).sum().item())
+            # decode the region (either layout; decode_wire checks prefixes, header counts, disjoint ranges) and fold
+            # what it says -- who passed, with which mean and visible set -- into one checksum
+            wv = _records.decode_wire(half[r * region_bytes:(r + 1) * region_bytes].cpu().numpy(), V, n, xparts)
+            idx = np.nonzero(wv["passed"])[0].astype(np.uint64)
+            with np.errstate(over="ignore"):                      # 64-bit wrap-around sums
+                body = int((idx * np.uint64(2654435761)).sum(dtype=np.uint64)
+                           + wv["avg"][wv["passed"]].view(np.uint64).sum(dtype=np.uint64)
+                           + wv["vis"].sum(dtype=np.uint64) + np.uint64(wv["used"]))
+            return torch.tensor([body % (1 << 62)], dtype=torch.int64, device=dev), int(sum(wv["kept"])), wv
+        mine, kept, mine_wv = region_sum(rank)
+        # ... and MY region says exactly what my own results say
+        keep_np = (out["count"] >= BOUND).cpu().numpy()
+        own_ok = bool(np.array_equal(mine_wv["passed"], keep_np) and
+                      np.array_equal(mine_wv["avg"][keep_np], out["avg"].cpu().numpy()[keep_np]) and
+                      np.array_equal(mine_wv["vis"][keep_np].astype(np.int64), out["vis_mask"].cpu().numpy()[keep_np]))
+        want_kept = int(keep_np.sum()) if own_ok else -1
         if world > 1:
             sums = torch.zeros(world, dtype=torch.int64, device=dev)
             dist.all_gather_into_tensor(sums, mine)
-            got = torch.cat([region_sum(r)[0] for r in range(world)])
+            got = torch.cat([mine if r == rank else region_sum(r)[0] for r in range(world)])
             okt = torch.tensor([int(torch.equal(sums, got) and kept == want_kept and kept > 0)], device=dev)
             dist.all_reduce(okt, op=dist.ReduceOp.MIN)
             exchange_ok = bool(okt.item())
@@ -601,6 +615,9 @@ def run_b200(args):
                     "note": "window bytes are reused from L1 by neighbouring hypotheses, so algorithmic bytes/s exceed HBM speed by design; "
                             "the binding unit is the L1 data pipe (ncu: l1tex__data_pipe_lsu_wavefronts 73-79 %), which the probe measures"}
             step_desc = "project + tile-order + score + publish accept decisions (minimal wire)"
+            if xparts > 1:
+                step_desc += (f"; {xparts} position ranges of the ordered batch, each its own K1 launch + publish on a stream of "
+                              "descending priority: the NVLink stores of a range run under the scoring of the ranges behind it")
             if world > 1:
                 step_desc += (" into every GPU's inbox over NVLink stores + one device-side barrier; every GPU holds the global "
                               f"candidate list ({world} x {n}) and scores its shard")
@@ -612,7 +629,8 @@ def run_b200(args):
                        "mode": w["mode"],
                        "l2": "flushed between timed steps by a 256 MiB fill (not timed); per-step CUDA events summed",
                        "launch": graph_note,
-                       "step": step_desc, "exchange": exchange, "exchange_verified": exchange_ok,
+                       "step": step_desc, "exchange": exchange, "exchange_parts": xparts if not mode_b else None,
+                       "exchange_verified": exchange_ok,
                        "rounds_verified": rounds_ok[0] if rounds_ok else None,
                        "rounds_check": ("%d patches in %d rounds, sharded == unsharded" % rounds_ok[1:]) if rounds_ok else None,
                        "kept_per_gpu_last_step": kept},

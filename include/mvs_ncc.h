@@ -333,6 +333,26 @@ int mvs_publish_accepted(mvs_ctx* ctx, int64_t N, const uint64_t* vis_mask, cons
                          int parity, void* stream);
 
 /*
+ * Overlap of the exchange with the scoring.  mvs_exchange_set_parts(ctx, P, min_batch) (1 <= P <= 8; the default 1 is
+ * off; min_batch <= 0: 2^17) makes mvs_score_publish -- and mvs_expand_run -- cut a shard of at least min_batch
+ * candidates into P consecutive POSITION ranges of the tile-ordered batch (anchor-tile ranges: the L1 reuse inside a
+ * range survives).  Range k is its own K1 launch followed by the publish of its accept decisions (compaction + NVLink
+ * stores) on a side stream of priority k, the last range on the caller's stream; the stream priorities make the GPU
+ * work through the ranges in order without draining between them, so the publish of range k runs while the ranges
+ * behind it are still being scored and only the last range's stores are exposed.  Such a round's region holds P
+ * sub-regions (one per range: words over all candidates, entries of the range's own) and says so in its header; the
+ * commit ORs them.  Results are identical for every P.  Call it with the same P on every GPU, BEFORE
+ * mvs_exchange_bytes sizes the inboxes.
+ * mvs_score_publish = mvs_score_batch(MVS_MODE_REFEXACT, on_device) + mvs_publish_accepted in one stream-ordered
+ * (CUDA-graph capturable) sequence; all data pointers DEVICE.
+ * Replaces: nothing in the reference (single process); the accept branch it feeds is MVS2.py:369,401-403.
+ */
+int mvs_exchange_set_parts(mvs_ctx* ctx, int parts, int64_t min_batch);
+int mvs_score_publish(mvs_ctx* ctx, int64_t N, const double* c, const int32_t* ref, double min_ncc, int wid,
+                      uint64_t* vis_mask, double* avg, int32_t* count, double* xy, const uint8_t* gate, int bound,
+                      void* const* peer_inbox, int rank, int world, int64_t capacity, int parity, void* stream);
+
+/*
  * Device-side barrier across the GPUs of the box: one tiny kernel, no host round trip, capturable in a
  * CUDA graph.  peer_flags: HOST array of `world` DEVICE pointers, entry g = GPU g's array of `world + 1`
  * uint64 words (slots 0..world-1: one flag per peer, slot world: that GPU's own epoch counter; ALL zero-initialised

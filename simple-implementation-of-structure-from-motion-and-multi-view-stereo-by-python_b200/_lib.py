@@ -44,6 +44,9 @@ SYMBOLS = {
     "mvs_round_candidates": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "mvs_exchange_bytes": (C.c_int64, [_P, C.c_int, C.c_int64]),
     "mvs_publish_accepted": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, C.c_int, _P, C.c_int, C.c_int, C.c_int64, C.c_int, _P]),
+    "mvs_exchange_set_parts": (C.c_int, [_P, C.c_int, C.c_int64]),
+    "mvs_score_publish": (C.c_int, [_P, C.c_int64, _P, _P, C.c_double, C.c_int, _P, _P, _P, _P, _P, C.c_int, _P, C.c_int, C.c_int,
+                                    C.c_int64, C.c_int, _P]),
     "mvs_p2p_barrier": (C.c_int, [_P, _P, C.c_int, C.c_int, _P]),
     "mvs_p2p_barrier_failed": (C.c_int, [_P, _P]),
     "mvs_expand_run": (C.c_int, [_P, _P, C.c_int64, _P, _P, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int64), _P]),

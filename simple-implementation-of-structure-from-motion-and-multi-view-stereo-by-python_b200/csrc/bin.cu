@@ -94,15 +94,18 @@ __global__ void __launch_bounds__(256)
 
 __global__ void __launch_bounds__(256)
     bin_scatter(int64_t N, const int32_t* __restrict__ hist_excl, const int32_t* __restrict__ key,
-                const int32_t* __restrict__ rank, const uint32_t* __restrict__ anchor, uint2* __restrict__ entry) {
+                const int32_t* __restrict__ rank, const uint32_t* __restrict__ anchor, uint2* __restrict__ entry,
+                uint8_t* __restrict__ part, int part_size) {
     for (int64_t h = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; h < N; h += (int64_t)gridDim.x * blockDim.x) {
         const int pos = hist_excl[key[h]] + rank[h];
         entry[pos] = make_uint2((uint32_t)h, anchor[h]);   // one 8-byte scattered store per hypothesis
+        // partitioned publish (exchange.cu): which position range -- i.e. which of K1's launches -- scores this hypothesis
+        if (part) part[h] = (uint8_t)(pos / part_size);
     }
 }
 
 int mvs_bin_hypotheses(mvs_ctx* ctx, int64_t N, const double* c, const int32_t* ref, int wid, bool sort, uint64_t* vis,
-                       double* avg, int32_t* count, double* xy, float* ncc, cudaStream_t s) {
+                       double* avg, int32_t* count, double* xy, float* ncc, cudaStream_t s, uint8_t* part, int64_t part_size) {
     int rc;
     if (N >= (1ll << 31)) {
         mvs_set_error("batches of 2^31 or more hypotheses are not supported (got %lld)", (long long)N);
@@ -136,7 +139,7 @@ int mvs_bin_hypotheses(mvs_ctx* ctx, int64_t N, const double* c, const int32_t* 
         if ((rc = mvs_exclusive_scan_i32(ctx->d_bin_hist, n_tiles + 1, ctx->d_bin_scan, d_total, s)) != MVS_OK) return rc;
         ctx->launches += mvs_scan_launches(n_tiles + 1);
         bin_scatter<<<(int)blocks, 256, 0, s>>>(N, ctx->d_bin_hist, ctx->d_bin_key, ctx->d_bin_rank, ctx->d_bin_anchor,
-                                                (uint2*)ctx->d_bin_entry);
+                                                (uint2*)ctx->d_bin_entry, part, (int)part_size);
         ctx->launches++;
     }
     MVS_CUDA_CHECK(cudaGetLastError());

@@ -19,17 +19,30 @@
 // MVS2.py:401-403 (fill cells for every hit, enqueue).
 #include "project.cuh"
 #include "scan.cuh"
+#include <stdlib.h>
 
 #define FULL 0xffffffffu
 #define XTILE 1024         // candidates per CTA of the publish kernels (256 threads x 4)
 
 struct WireLayout {
-    int64_t region_bytes;  // one source rank's region
-    int64_t ent_off;       // byte offset of the entries inside a region
+    int64_t region_bytes;  // one source rank's region (large enough for either layout below)
+    int64_t ent_off;       // byte offset of the entries inside a region / a part's sub-region
     int64_t capacity;      // candidates per region
+    int64_t sub_bytes;     // partitioned layout: bytes of one part's sub-region {header, words over ALL candidates, entries}
+    int64_t part_cap;      // partitioned layout: positions (hence entries at most) per part
     int wb;                // bytes per entry
     int mw;
+    int parts;             // the context's mvs_exchange_set_parts value (1: single layout only)
 };
+
+// A region is written in ONE of two layouts, chosen by the sender round by round and named in its header
+// (hdr[1] = n | parts_used << 48):
+//   single       header | words | entries                                  (parts_used = 0 or 1)
+//   partitioned  P sub-regions of sub_bytes, one per K1 launch (position range of the ordered batch); the words of
+//                sub-region k cover ALL n candidates but only carry the bits of the candidates scored by launch k,
+//                its entries are those candidates' in candidate order.  passed(i) = OR over the parts.
+#define WIRE_PARTS_SHIFT 48
+#define WIRE_N_MASK ((1ll << WIRE_PARTS_SHIFT) - 1)
 
 __host__ __device__ static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
@@ -41,7 +54,27 @@ static WireLayout wire_layout(const mvs_ctx* ctx, int64_t capacity) {
     const int64_t nw = (capacity + 31) / 32;
     L.ent_off = align_up(16 + 8 * nw, 256);
     L.region_bytes = align_up(L.ent_off + capacity * L.wb, 256);
+    L.parts = ctx->xparts > 1 ? ctx->xparts : 1;
+    L.part_cap = align_up((capacity + L.parts - 1) / L.parts, 1024);
+    L.sub_bytes = align_up(L.ent_off + L.part_cap * L.wb, 256);
+    if (L.parts > 1 && L.parts * L.sub_bytes > L.region_bytes) L.region_bytes = L.parts * L.sub_bytes;
     return L;
+}
+
+int64_t mvs_exchange_sub_bytes(const mvs_ctx* ctx, int64_t capacity) { return wire_layout(ctx, capacity).sub_bytes; }
+
+// positions per K1 launch for a batch of N hypotheses in P parts (a multiple of every K1 variant's chunk)
+static inline int64_t part_size_of(int64_t N, int P) { return align_up((N + P - 1) / P, 1024); }
+
+extern "C" int mvs_exchange_set_parts(mvs_ctx* ctx, int parts, int64_t min_batch) {
+    if (!ctx) { mvs_set_error("mvs_exchange_set_parts: null context"); return MVS_ERR_ARG; }
+    if (parts < 1 || parts > MVS_MAX_PARTS) {
+        mvs_set_error("mvs_exchange_set_parts: 1 <= parts <= %d", MVS_MAX_PARTS);
+        return MVS_ERR_ARG;
+    }
+    ctx->xparts = parts;
+    ctx->xparts_min = min_batch > 0 ? min_batch : (1ll << 17);
+    return MVS_OK;
 }
 
 extern "C" int64_t mvs_exchange_bytes(const mvs_ctx* ctx, int world, int64_t capacity) {
@@ -54,30 +87,47 @@ struct PeerInbox {
     int world;
 };
 
-__device__ __forceinline__ bool pass_flag(const int32_t* count, const uint8_t* gate, int bound, int64_t i, int64_t N) {
-    return i < N && count[i] >= bound && (gate == nullptr || gate[i] != 0);
+// which candidates a publish launch covers: all (used <= 1) or those of position range `id`
+struct PartSel {
+    const uint8_t* part;   // [N] position range of every candidate (ordered batches), nullptr: range = index / size
+    int64_t size;
+    int id, used;
+};
+
+__device__ __forceinline__ bool pass_flag(const int32_t* count, const uint8_t* gate, int bound, int64_t i, int64_t N,
+                                          const PartSel& S) {
+    if (i >= N) return false;
+    // (membership first: the results of the other ranges may still be in flight)
+    if (S.used > 1 && (S.part ? (int)S.part[i] : (int)(i / S.size)) != S.id) return false;
+    return count[i] >= bound && (gate == nullptr || gate[i] != 0);
 }
 
 // Per-tile counts of passed candidates AND, in the CTA that finishes last (ticket counter), the exclusive scan of the
 // tile counts + the header {kept, n} to every inbox: one launch instead of two.
 __global__ void __launch_bounds__(256)
     publish_count_scan(const int32_t* __restrict__ count, const uint8_t* __restrict__ gate, int bound, int64_t N,
-                       int32_t* __restrict__ tile_counts, int T, const PeerInbox P, unsigned* __restrict__ ticket) {
+                       int32_t* __restrict__ tile_counts, int T, const PeerInbox P, unsigned* __restrict__ ticket,
+                       const PartSel S) {
     __shared__ int warp_sum[8];
     __shared__ bool s_last;
     __shared__ long long s_carry;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int64_t base = (int64_t)blockIdx.x * XTILE;
-    int k = 0;
+    for (int tile = blockIdx.x; tile < T; tile += gridDim.x) {     // (a few CTAs walk all tiles when the publish shares the GPU with K1)
+        const int64_t base = (int64_t)tile * XTILE;
+        int k = 0;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) k += pass_flag(count, gate, bound, base + j * 256 + threadIdx.x, N) ? 1 : 0;
-    k = __reduce_add_sync(FULL, k);
-    if (lane == 0) warp_sum[w] = k;
-    __syncthreads();
+        for (int j = 0; j < 4; ++j) k += pass_flag(count, gate, bound, base + j * 256 + threadIdx.x, N, S) ? 1 : 0;
+        k = __reduce_add_sync(FULL, k);
+        if (lane == 0) warp_sum[w] = k;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int sum = 0;
+            for (int q = 0; q < 8; ++q) sum += warp_sum[q];
+            tile_counts[tile] = sum;
+        }
+        __syncthreads();
+    }
     if (threadIdx.x == 0) {
-        int sum = 0;
-        for (int q = 0; q < 8; ++q) sum += warp_sum[q];
-        if ((int)blockIdx.x < T) tile_counts[blockIdx.x] = sum;
         __threadfence();
         s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
         s_carry = 0;
@@ -109,7 +159,7 @@ __global__ void __launch_bounds__(256)
     if (threadIdx.x < P.world) {
         int64_t* hdr = reinterpret_cast<int64_t*>(P.base[threadIdx.x]);
         hdr[0] = s_carry;
-        hdr[1] = N;
+        hdr[1] = N | ((int64_t)(S.used > 1 ? S.used : 0) << WIRE_PARTS_SHIFT);
     }
     if (threadIdx.x == 0) *ticket = 0u;                    // ready for the next launch
 }
@@ -118,17 +168,18 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     publish_scatter(const int32_t* __restrict__ count, const uint8_t* __restrict__ gate, int bound, int64_t N,
                     const int32_t* __restrict__ tile_offsets, const uint64_t* __restrict__ vis, const double* __restrict__ avg,
-                    const PeerInbox P, const WireLayout L) {
+                    const PeerInbox P, const WireLayout L, const PartSel S, int T) {
     extern __shared__ __align__(16) uint8_t s_ent[];       // 256 entries
     __shared__ int warp_base[8];
     __shared__ __align__(16) uint2 s_words[32];            // the tile's 32 words
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int64_t base = (int64_t)blockIdx.x * XTILE;
-    int64_t out = tile_offsets[blockIdx.x];
     const int ent_words = L.wb >> 3;
+    for (int tile = blockIdx.x; tile < T; tile += gridDim.x) {
+    const int64_t base = (int64_t)tile * XTILE;
+    int64_t out = tile_offsets[tile];
     for (int j = 0; j < 4; ++j) {
         const int64_t i = base + j * 256 + threadIdx.x;
-        const bool k = pass_flag(count, gate, bound, i, N);
+        const bool k = pass_flag(count, gate, bound, i, N, S);
         const unsigned b = __ballot_sync(FULL, k);
         if (lane == 0) warp_base[w] = __popc(b);
         __syncthreads();
@@ -172,35 +223,164 @@ __global__ void __launch_bounds__(256)
             for (int d = 0; d < P.world; ++d) reinterpret_cast<uint4*>(P.base[d] + 16 + 8 * w0)[threadIdx.x] = wv;
         }
     }
+    __syncthreads();                                       // s_words / s_ent are reused by the next tile
+    }
 }
 
-int mvs_launch_publish(mvs_ctx* ctx, int64_t N, const uint64_t* vis, const double* avg, const int32_t* count,
-                       const uint8_t* gate, int bound, void* const* peer_inbox, int rank, int world, int64_t capacity,
-                       int parity, cudaStream_t s) {
+// part_id / parts_used / part / part_size: the position range this launch covers (parts_used <= 1: everything, single layout)
+static int launch_publish_part(mvs_ctx* ctx, int64_t N, const uint64_t* vis, const double* avg, const int32_t* count,
+                               const uint8_t* gate, int bound, void* const* peer_inbox, int rank, int world, int64_t capacity,
+                               int parity, int part_id, int parts_used, const uint8_t* part, int64_t part_size, cudaStream_t s,
+                               int max_ctas = 0) {
     const WireLayout L = wire_layout(ctx, capacity);
     PeerInbox P;
     memset(&P, 0, sizeof(P));
     P.world = world;
     for (int d = 0; d < world; ++d)
-        P.base[d] = (uint8_t*)peer_inbox[d] + ((int64_t)(parity & 1) * world + rank) * L.region_bytes;
+        P.base[d] = (uint8_t*)peer_inbox[d] + ((int64_t)(parity & 1) * world + rank) * L.region_bytes +
+                    (parts_used > 1 ? (int64_t)part_id * L.sub_bytes : 0);
+    PartSel S;
+    S.part = part; S.size = part_size > 0 ? part_size : 1; S.id = part_id; S.used = parts_used > 1 ? parts_used : 1;
+    const int T = (int)((N + XTILE - 1) / XTILE);
+    int32_t* tiles = ctx->d_tiles + (size_t)part_id * (T + 1);          // (sized by the caller for all parts)
+    unsigned* ticket = (unsigned*)ctx->d_ticket + part_id;
+    // a publish that shares the GPU with K1 (the side stream of the overlapped exchange) runs as a FEW persistent CTAs:
+    // K1's two CTAs per SM hold the whole register file, so every SM a publish CTA lands on scores at half occupancy
+    // meanwhile; NVLink-rate stores need only a few SMs
+    int grid = T > 0 ? T : 1;                              // T == 0: an empty shard
+    if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+    publish_count_scan<<<grid, 256, 0, s>>>(count, gate, bound, N, tiles, T, P, ticket, S);
+    ctx->launches++;
+    if (T > 0) {
+        const size_t smem = (size_t)256 * L.wb;
+        if (smem > 40 * 1024) MVS_CUDA_CHECK(cudaFuncSetAttribute(publish_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        publish_scatter<<<grid, 256, smem, s>>>(count, gate, bound, N, tiles, vis, avg, P, L, S, T);
+        ctx->launches++;
+    }
+    MVS_CUDA_CHECK(cudaGetLastError());
+    return MVS_OK;
+}
+
+static int ensure_publish_scratch(mvs_ctx* ctx, int64_t N, int parts, cudaStream_t s) {
     const int T = (int)((N + XTILE - 1) / XTILE);
     int rc;
-    if ((rc = mvs_ensure((void**)&ctx->d_tiles, &ctx->tile_bytes, sizeof(int32_t) * (size_t)(T + 1), "publish scratch")) != MVS_OK)
+    if ((rc = mvs_ensure((void**)&ctx->d_tiles, &ctx->tile_bytes, sizeof(int32_t) * (size_t)(T + 1) * parts, "publish scratch")) != MVS_OK)
         return rc;
     if (!ctx->d_ticket) {
         MVS_CUDA_CHECK(cudaMalloc(&ctx->d_ticket, 64));
         MVS_CUDA_CHECK(cudaMemsetAsync(ctx->d_ticket, 0, 64, s));
     }
-    publish_count_scan<<<T > 0 ? T : 1, 256, 0, s>>>(count, gate, bound, N, ctx->d_tiles, T, P, (unsigned*)ctx->d_ticket);   // T == 0: an empty shard
-    ctx->launches++;
-    if (T > 0) {
-        const size_t smem = (size_t)256 * L.wb;
-        if (smem > 40 * 1024) MVS_CUDA_CHECK(cudaFuncSetAttribute(publish_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        publish_scatter<<<T, 256, smem, s>>>(count, gate, bound, N, ctx->d_tiles, vis, avg, P, L);
-        ctx->launches++;
-    }
-    MVS_CUDA_CHECK(cudaGetLastError());
     return MVS_OK;
+}
+
+int mvs_launch_publish(mvs_ctx* ctx, int64_t N, const uint64_t* vis, const double* avg, const int32_t* count,
+                       const uint8_t* gate, int bound, void* const* peer_inbox, int rank, int world, int64_t capacity,
+                       int parity, cudaStream_t s) {
+    int rc;
+    if ((rc = ensure_publish_scratch(ctx, N, 1, s)) != MVS_OK) return rc;
+    return launch_publish_part(ctx, N, vis, avg, count, gate, bound, peer_inbox, rank, world, capacity, parity, 0, 1, nullptr, 1, s);
+}
+
+// ---------------------------------------------------------------------------------------
+// Score + publish of one shard with the exchange OVERLAPPED with the scoring.  The tile-ordered batch is cut into P
+// consecutive position ranges (anchor-tile ranges, so the L1 reuse inside a range survives); range k is its own K1
+// launch followed by the publish of its accept decisions -- compaction + NVLink stores into every GPU's inbox -- on
+// side stream k, the last range on the caller's stream.  The launches do not depend on each other, so they are all
+// enqueued at once and the hardware works through them back to back WITHOUT draining the GPU in between (the CTAs of
+// the next launch fill the slots the previous one frees); the P launches share the grid cap of one launch, so the
+// batch is scored by as many CTAs as before.  The publish of a finished range then runs while the other ranges are
+// still being scored, and only the publish of the range that finishes last is exposed.  Measured on one B200 (2^20
+// hypotheses, nothing to hide there): 0.399 ms per step plain, 0.408 with two ranges, 0.423 with four.  Measured and
+// rejected: the ranges as consecutive launches on ONE stream (every extra launch costs ~40 us of drain and ramp-up:
+// K1 0.326 -> 0.367 ms for two ranges); ONE K1 launch whose warps report finished chunks into per-range counters for
+// a gate kernel on the side stream (the __threadfence before every report costs as much: 0.326 -> 0.363 ms); side
+// streams of DESCENDING priority (the high-priority publish CTAs fragment the register file K1's two CTAs per SM
+// fill completely: 0.420 vs 0.408 ms); range launches of one chunk per CTA (0.438 ms: 1.7 chunks per CTA through the
+// shared grid cap amortise the CTA start-up).
+// The fork / join is stream-ordered (events), so the sequence is capturable in a CUDA graph like the plain one.
+// P <= 1, small shards: the plain sequence.
+// ---------------------------------------------------------------------------------------
+int mvs_launch_score_publish(mvs_ctx* ctx, int64_t N, const double* c, const int32_t* ref, double thr, int wid, uint64_t* vis,
+                             double* avg, int32_t* count, double* xy, const uint8_t* gate, int bound, void* const* peer_inbox,
+                             int rank, int world, int64_t capacity, int parity, cudaStream_t s) {
+    int rc;
+    const int P = ctx->xparts;
+    if (P <= 1 || N < ctx->xparts_min || N < 2048ll * P || N < MVS_SORT_MIN || ctx->probe_gather) {
+        if (N > 0 && (rc = mvs_launch_score_refexact(ctx, N, c, ref, thr, wid, vis, avg, count, xy, nullptr, s)) != MVS_OK) return rc;
+        return mvs_launch_publish(ctx, N, vis, avg, count, gate, bound, peer_inbox, rank, world, capacity, parity, s);
+    }
+    if (wid < 1 || wid > 7) {
+        mvs_set_error("wid %d not supported (1..7)", wid);
+        return MVS_ERR_ARG;
+    }
+    if ((rc = mvs_build_window_maps(ctx, wid, s)) != MVS_OK) return rc;
+    if ((rc = ensure_publish_scratch(ctx, N, P, s)) != MVS_OK) return rc;
+    if ((rc = mvs_ensure((void**)&ctx->d_bin_part, &ctx->bin_part_bytes, (size_t)N, "position ranges")) != MVS_OK) return rc;
+    static int xmode = -1;                                 // MVS_XMODE (measurement knob): 0 = every side stream at the default (lowest)
+    if (xmode < 0) {                                       // priority, 1 = side streams of descending priority (range 0 highest)
+        const char* e = getenv("MVS_XMODE");
+        xmode = e ? atoi(e) : 0;
+    }
+    if (!ctx->x_fork) {
+        int lo = 0, hi = 0;                                // (numerically: hi <= lo, hi = the highest priority)
+        MVS_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        for (int i = 0; i < MVS_MAX_PARTS; ++i) {
+            int prio = hi + i < lo ? hi + i : lo;
+            if (xmode != 1) prio = lo;
+            MVS_CUDA_CHECK(cudaStreamCreateWithPriority(&ctx->x_side[i], cudaStreamNonBlocking, prio));
+            MVS_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->x_ev[i], cudaEventDisableTiming));
+        }
+        MVS_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->x_fork, cudaEventDisableTiming));
+    }
+    const int64_t S = part_size_of(N, P);                  // positions per range: a multiple of 1024, hence of K1's chunk
+    if ((rc = mvs_bin_hypotheses(ctx, N, c, ref, wid, true, vis, avg, count, xy, nullptr, s, ctx->d_bin_part, S)) != MVS_OK) return rc;
+    const int pslot = (int)(ctx->prof_n % MVS_PROF_RING);
+    if (ctx->profile) MVS_CUDA_CHECK(cudaEventRecord(ctx->prof_ev[2 * pslot], s));
+    MVS_CUDA_CHECK(cudaEventRecord(ctx->x_fork, s));
+    ctx->k1_share = P;                                     // the P range launches share the grid cap of one launch
+    // ---- ranges 0 .. P-2 on the side streams (enqueued in order: a tool that serialises kernels still runs them in order)
+    for (int k = 0; k + 1 < P; ++k) {
+        cudaStream_t q = ctx->x_side[k];
+        MVS_CUDA_CHECK(cudaStreamWaitEvent(q, ctx->x_fork, 0));
+        if ((rc = mvs_launch_k1(ctx, N, ref, thr, wid, vis, avg, count, nullptr, true, (int64_t)k * S, (int64_t)(k + 1) * S, q)) != MVS_OK) {
+            ctx->k1_share = 0;
+            return rc;
+        }
+        if ((rc = launch_publish_part(ctx, N, vis, avg, count, gate, bound, peer_inbox, rank, world, capacity, parity, k, P,
+                                      ctx->d_bin_part, S, q)) != MVS_OK)
+            return rc;
+        MVS_CUDA_CHECK(cudaEventRecord(ctx->x_ev[k], q));
+    }
+    // ---- the last range on the caller's stream, then join
+    rc = mvs_launch_k1(ctx, N, ref, thr, wid, vis, avg, count, nullptr, true, (int64_t)(P - 1) * S, N, s);
+    ctx->k1_share = 0;
+    if (rc != MVS_OK) return rc;
+    if (ctx->profile) {                                    // K1 alone: the lowest-priority range ends last
+        MVS_CUDA_CHECK(cudaEventRecord(ctx->prof_ev[2 * pslot + 1], s));
+        ctx->prof_n++;
+    }
+    if ((rc = launch_publish_part(ctx, N, vis, avg, count, gate, bound, peer_inbox, rank, world, capacity, parity, P - 1, P,
+                                  ctx->d_bin_part, S, s)) != MVS_OK)
+        return rc;
+    for (int k = 0; k + 1 < P; ++k) MVS_CUDA_CHECK(cudaStreamWaitEvent(s, ctx->x_ev[k], 0));
+    return MVS_OK;
+}
+
+extern "C" int mvs_score_publish(mvs_ctx* ctx, int64_t N, const double* c, const int32_t* ref, double min_ncc, int wid,
+                                 uint64_t* vis_mask, double* avg, int32_t* count, double* xy, const uint8_t* gate, int bound,
+                                 void* const* peer_inbox, int rank, int world, int64_t capacity, int parity, void* stream) {
+    if (!ctx) { mvs_set_error("mvs_score_publish: null context"); return MVS_ERR_ARG; }
+    if (N < 0 || capacity < N || !peer_inbox || world < 1 || world > MVS_MAX_PEERS || rank < 0 || rank >= world ||
+        (N > 0 && (!c || !ref || !vis_mask || !avg || !count))) {
+        mvs_set_error("mvs_score_publish: need 0 <= N <= capacity, 1 <= world <= %d, 0 <= rank < world, the inbox table, c, ref "
+                      "and vis_mask, avg, count", MVS_MAX_PEERS);
+        return MVS_ERR_ARG;
+    }
+    for (int d = 0; d < world; ++d)
+        if (!peer_inbox[d]) { mvs_set_error("mvs_score_publish: null inbox pointer %d", d); return MVS_ERR_ARG; }
+    MVS_CUDA_CHECK(cudaSetDevice(ctx->device));
+    return mvs_launch_score_publish(ctx, N, c, ref, min_ncc, wid, vis_mask, avg, count, xy, gate, bound, peer_inbox, rank, world,
+                                    capacity, parity, (cudaStream_t)stream);
 }
 
 extern "C" int mvs_publish_accepted(mvs_ctx* ctx, int64_t N, const uint64_t* vis_mask, const double* avg, const int32_t* count,
@@ -288,7 +468,8 @@ extern "C" int mvs_p2p_barrier(mvs_ctx* ctx, void* const* peer_flags, int rank, 
 
 // 0 = fine, 1 = a barrier gave up waiting for a peer since the context was created (synchronises `stream`)
 extern "C" int mvs_p2p_barrier_failed(mvs_ctx* ctx, void* stream) {
-    if (!ctx || !ctx->d_barrier_state) return 0;
+    if (!ctx) return 0;
+    if (!ctx->d_barrier_state) return 0;
     int e = 0;
     if (cudaMemcpyAsync(&e, (uint8_t*)ctx->d_barrier_state + 8, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream) != cudaSuccess ||
         cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess)
@@ -319,11 +500,17 @@ __device__ __forceinline__ bool wire_passed(const WireView& Wv, const WireLayout
     while (r + 1 < Wv.world && i >= Wv.begin[r + 1]) ++r;
     const int64_t j = i - Wv.begin[r];
     region = Wv.half + (int64_t)r * L.region_bytes;
-    const uint2 wd = *reinterpret_cast<const uint2*>(region + 16 + 8 * (j >> 5));
-    bits = wd.x;
-    prefix = wd.y;
     bitpos = (int)(j & 31);
-    return (bits >> bitpos) & 1u;
+    // the sender's layout of this round: single, or one sub-region per K1 launch (a candidate passed in at most one)
+    const int used = (int)(*reinterpret_cast<const int64_t*>(region + 8) >> WIRE_PARTS_SHIFT);
+    for (int k = 0;;) {
+        const uint2 wd = *reinterpret_cast<const uint2*>(region + 16 + 8 * (j >> 5));
+        bits = wd.x;
+        prefix = wd.y;
+        if ((bits >> bitpos) & 1u) return true;
+        if (++k >= used) return false;
+        region += L.sub_bytes;
+    }
 }
 
 __global__ void __launch_bounds__(256)

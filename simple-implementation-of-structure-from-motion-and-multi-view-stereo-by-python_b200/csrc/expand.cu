@@ -494,17 +494,26 @@ int mvs_launch_publish(mvs_ctx* ctx, int64_t N, const uint64_t* vis, const doubl
                        int parity, cudaStream_t s);
 int mvs_launch_commit_wire(mvs_ctx* ctx, const void* inbox_local, int world, int64_t capacity, int parity, int64_t M,
                            void* next_frontier, int64_t* d_n_next, cudaStream_t s);
+int64_t mvs_exchange_sub_bytes(const mvs_ctx* ctx, int64_t capacity);
 
 // Everything the host needs to know about a round, written by ONE tiny kernel straight into pinned (device-mapped)
 // host memory: {accepted, candidates of the next round, kept per rank, barrier error flag}.  Replaces three small
 // device->host copies (and a fourth for the barrier flag), each of which cost a few microseconds of a ~160 us round.
 __global__ void __launch_bounds__(32) round_report(const int64_t* __restrict__ d_n_next, const int64_t* __restrict__ d_M_next,
-                                                   const uint8_t* __restrict__ inbox_half, int64_t region_bytes, int world,
-                                                   const int* __restrict__ barrier_err, volatile int64_t* __restrict__ host_out) {
+                                                   const uint8_t* __restrict__ inbox_half, int64_t region_bytes, int64_t sub_bytes,
+                                                   int world, const int* __restrict__ barrier_err,
+                                                   volatile int64_t* __restrict__ host_out) {
     const int t = threadIdx.x;
     if (t == 0) host_out[0] = *d_n_next;
     if (t == 1) host_out[1] = d_M_next ? *d_M_next : 0;
-    if (t >= 2 && t < 2 + world) host_out[t] = *reinterpret_cast<const int64_t*>(inbox_half + (int64_t)(t - 2) * region_bytes);
+    if (t >= 2 && t < 2 + world) {
+        // kept candidates of rank t - 2: one header, or one per position range of a partitioned publish
+        const uint8_t* reg = inbox_half + (int64_t)(t - 2) * region_bytes;
+        const int used = (int)(reinterpret_cast<const int64_t*>(reg)[1] >> 48);
+        int64_t kept = 0;
+        for (int k = 0; k < (used > 1 ? used : 1); ++k) kept += *reinterpret_cast<const int64_t*>(reg + (int64_t)k * sub_bytes);
+        host_out[t] = kept;
+    }
     if (t == 2 + world) host_out[t] = barrier_err ? (int64_t)*barrier_err : 0;
     __threadfence_system();
 }
@@ -633,7 +642,6 @@ extern "C" int mvs_expand_run(mvs_ctx* ctx, const void* seeds, int64_t n_seeds, 
             ctx->n_cand = M;
             // ---- this GPU's shard: score, gate, publish
             const int64_t begin = (M * rank) / world, end = (M * (rank + 1)) / world;
-            if ((rc = round_score_shard(ctx, frontier, begin, end, prm->min_ncc, prm->wid, prm->scale, s, true)) != MVS_OK) return rc;
             void* local_tab[1];
             void* const* inbox_tab = prm->peer_inbox;
             const void* inbox_local;
@@ -647,8 +655,12 @@ extern "C" int mvs_expand_run(mvs_ctx* ctx, const void* seeds, int64_t n_seeds, 
                 inbox_local = prm->peer_inbox[rank];
             }
             const int parity = (int)(k & 1);
-            if ((rc = mvs_launch_publish(ctx, end - begin, ctx->cand_vis + mw * begin, ctx->cand_avg + begin, ctx->cand_count + begin,
-                                         ctx->cand_gate + begin, prm->bound, inbox_tab, rank, world, shard_cap, parity, s)) != MVS_OK)
+            // score + publish (expand_geometry already wrote the gate); large shards with mvs_exchange_set_parts(P > 1):
+            // K1 in P launches, the publish of one position range under the scoring of the next
+            if ((rc = mvs_launch_score_publish(ctx, end - begin, ctx->cand_c + 3 * begin, ctx->cand_ref + begin, prm->min_ncc, prm->wid,
+                                               ctx->cand_vis + mw * begin, ctx->cand_avg + begin, ctx->cand_count + begin,
+                                               ctx->cand_xy + 2 * begin, ctx->cand_gate + begin, prm->bound, inbox_tab, rank, world,
+                                               shard_cap, parity, s)) != MVS_OK)
                 return rc;
             if (world > 1 && (rc = mvs_p2p_barrier(ctx, prm->peer_flags, rank, world, s)) != MVS_OK) return rc;
             // ---- commit (identical on every GPU): next frontier appended to the output buffer
@@ -665,7 +677,7 @@ extern "C" int mvs_expand_run(mvs_ctx* ctx, const void* seeds, int64_t n_seeds, 
             // ---- one read-back per round
             const int64_t region_bytes = mvs_exchange_bytes(ctx, world, shard_cap) / (2 * world);
             round_report<<<1, 32, 0, s>>>(d_n_next, d_M_next, (const uint8_t*)inbox_local + (size_t)parity * world * region_bytes,
-                                          region_bytes, world,
+                                          region_bytes, mvs_exchange_sub_bytes(ctx, shard_cap), world,
                                           (world > 1 && ctx->d_barrier_state) ? (const int*)((const uint8_t*)ctx->d_barrier_state + 8) : nullptr,
                                           h_back);
             ctx->launches++;

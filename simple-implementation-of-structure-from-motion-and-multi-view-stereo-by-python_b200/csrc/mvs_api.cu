@@ -273,9 +273,14 @@ extern "C" int mvs_destroy(mvs_ctx* ctx) {
                     ctx->cand_gate};
     for (void* b : bufs)
         if (b) cudaFree(b);
-    void* more2[] = {ctx->d_out, ctx->d_inbox, ctx->d_round_n, ctx->d_barrier_state, ctx->d_ticket, ctx->d_live};
+    void* more2[] = {ctx->d_out, ctx->d_inbox, ctx->d_round_n, ctx->d_barrier_state, ctx->d_ticket, ctx->d_live, ctx->d_bin_part};
     for (void* b : more2)
         if (b) cudaFree(b);
+    for (int i = 0; i < 8; ++i) {
+        if (ctx->x_side[i]) cudaStreamDestroy(ctx->x_side[i]);
+        if (ctx->x_ev[i]) cudaEventDestroy(ctx->x_ev[i]);
+    }
+    if (ctx->x_fork) cudaEventDestroy(ctx->x_fork);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     for (int i = 0; i < 2; ++i)
         if (ctx->ev_round[i]) cudaEventDestroy(ctx->ev_round[i]);

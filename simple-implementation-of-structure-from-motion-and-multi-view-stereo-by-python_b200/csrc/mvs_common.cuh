@@ -125,7 +125,16 @@ struct mvs_ctx {
     int64_t* d_round_n;
     size_t round_n_bytes;
     void* d_barrier_state;            // {u64 reserved, int error}
-    void* d_ticket;                   // last-CTA ticket of publish_count_scan
+    void* d_ticket;                   // last-CTA tickets of publish_count_scan (one per part)
+    // overlapped exchange (mvs_exchange_set_parts): one K1 launch + publish per position range, range k on side stream k
+    // (descending priority), the last range on the caller's stream
+    int xparts;                       // 1 = off
+    int k1_share;                     // > 1 while the range launches of one batch are being enqueued (K1's grid cap is shared)
+    int64_t xparts_min;               // smallest shard that is partitioned
+    uint8_t* d_bin_part;              // [N] position range of every hypothesis of the current ordered batch
+    size_t bin_part_bytes;
+    cudaStream_t x_side[8];
+    cudaEvent_t x_ev[8], x_fork;
     uint8_t* d_live;                  // [F, V] surviving diagonals of every (frontier patch, view), count pass -> emit pass
     size_t live_bytes;
     void* h_pinned;                   // small pinned read-back area
@@ -154,8 +163,20 @@ int mvs_launch_score_refexact(mvs_ctx* ctx, int64_t N, const double* c, const in
 int mvs_build_window_maps(mvs_ctx* ctx, int wid, cudaStream_t s);
 // project + validate every hypothesis (writes xy and, for rejected ones, the empty result),
 // optionally order them by anchor tile; leaves anchors / ordered entries in ctx->d_bin_*
+// part != nullptr (ordered batches only): part[h] = ordered position of hypothesis h / part_size
 int mvs_bin_hypotheses(mvs_ctx* ctx, int64_t N, const double* c, const int32_t* ref, int wid, bool sort, uint64_t* vis,
-                       double* avg, int32_t* count, double* xy, float* ncc, cudaStream_t s);
+                       double* avg, int32_t* count, double* xy, float* ncc, cudaStream_t s, uint8_t* part = nullptr,
+                       int64_t part_size = 1);
+// K1 alone over positions [p0, p1) of the batch mvs_bin_hypotheses left in the context (sort as passed there)
+int mvs_launch_k1(mvs_ctx* ctx, int64_t N, const int32_t* ref, double thr, int wid, uint64_t* vis, double* avg,
+                  int32_t* count, float* ncc, bool sort, int64_t p0, int64_t p1, cudaStream_t s);
+// score + publish of one shard; with mvs_exchange_set_parts(P > 1) every position range of the ordered batch is its own
+// K1 launch on a stream of its own priority, and the accept decisions of range k travel over NVLink while the ranges
+// behind it are still being scored (exchange.cu)
+int mvs_launch_score_publish(mvs_ctx* ctx, int64_t N, const double* c, const int32_t* ref, double thr, int wid, uint64_t* vis,
+                             double* avg, int32_t* count, double* xy, const uint8_t* gate, int bound, void* const* peer_inbox,
+                             int rank, int world, int64_t capacity, int parity, cudaStream_t s);
+#define MVS_MAX_PARTS 8
 int mvs_launch_score_pmvs(mvs_ctx* ctx, int64_t N, const double* c, const double* nrm, const int32_t* ref,
                           const uint64_t* cand, double thr, int mu, int flags, int group, int bound, uint64_t* vis,
                           double* avg, int32_t* count, double* xy, float* ncc, int32_t* best_idx, double* best_avg,

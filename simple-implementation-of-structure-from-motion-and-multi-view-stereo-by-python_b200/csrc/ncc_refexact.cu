@@ -983,6 +983,22 @@ __global__ void __launch_bounds__(256, MINB)
 #define MVS_K6_MINB 2          // resident CTAs per SM: measured 0.364 ms (2: 128 registers, no spills) / 0.382 (3) / 0.470 (4) per 2^20 hypotheses
 #endif
 
+// CTAs of a K1 launch: at most 8 per resident slot (the CTAs walk the chunks with a grid stride); a launch that is one of
+// ctx->k1_share concurrent range launches of the same batch (overlapped exchange) gets its share of that cap, so that
+// the batch as a whole is scored by the same number of CTAs as a single launch.  MVS_K1_CAPMUL: tuning knob.
+static int64_t k1_grid(const mvs_ctx* ctx, int64_t want, int minb) {
+    static int mul = 0;
+    if (mul == 0) {
+        const char* e = getenv("MVS_K1_CAPMUL");
+        mul = e ? atoi(e) : 8;
+        if (mul < 1) mul = 8;
+    }
+    int64_t cap = (int64_t)ctx->sm_count * minb * mul;
+    if (ctx->k1_share > 1) cap = (cap + ctx->k1_share - 1) / ctx->k1_share;
+    if (cap < 1) cap = 1;
+    return want < cap ? want : cap;
+}
+
 template <int WID, int GS, int MINB = MVS_K6_MINB>
 static int launch_gather6(mvs_ctx* ctx, const ScoreArgs& A, int64_t N, const uint32_t* anchors, const uint2* entries,
                           cudaStream_t s) {
@@ -994,8 +1010,7 @@ static int launch_gather6(mvs_ctx* ctx, const ScoreArgs& A, int64_t N, const uin
     }
     const int64_t chunk = 32 * (int64_t)per;
     const int64_t want = (N + chunk - 1) / chunk;
-    const int64_t cap = (int64_t)ctx->sm_count * MINB * 8;
-    const int blocks = (int)(want < cap ? want : cap);
+    const int blocks = (int)k1_grid(ctx, want, MINB);
     if (ctx->probe_gather)
         gather_probe6<WID, GS, MINB><<<blocks, 256, 0, s>>>(A, N, anchors, entries, (uint32_t*)ctx->d_bin_hist, per);
     else if (A.ncc_out)
@@ -1026,8 +1041,7 @@ static int launch_gather_gs(mvs_ctx* ctx, const ScoreArgs& A, int64_t N, const u
     auto kern = A.ncc_out ? ncc_score_gather<WID, LPH, GS, MINB, true, UNR> : ncc_score_gather<WID, LPH, GS, MINB, false, UNR>;
     const int64_t chunk = 8 * (32 / LPH) * 2 * MVS_K1_ITERS;
     const int64_t want = (N + chunk - 1) / chunk;
-    const int64_t cap = (int64_t)ctx->sm_count * MINB * 8;
-    const int blocks = (int)(want < cap ? want : cap);
+    const int blocks = (int)k1_grid(ctx, want, MINB);
     if (ctx->probe_gather)                                 // measurement hook: loads only, no results (mvs_probe_gather)
         gather_probe<WID, LPH, GS, MINB><<<blocks, 256, 0, s>>>(A, N, anchors, entries, (uint32_t*)ctx->d_bin_hist);
     else
@@ -1103,6 +1117,40 @@ static int launch_gather(mvs_ctx* ctx, const ScoreArgs& A, int64_t N, const uint
     return launch_gather_gs<WID, 32, 0>(ctx, A, N, anchors, entries, s);
 }
 
+// K1 alone over positions [p0, p1) of the batch mvs_bin_hypotheses left in ctx->d_bin_* (`sort` as passed there).  No
+// profiling bracket: mvs_launch_score_refexact and the overlapped score + publish (exchange.cu) wrap it.  A sub-range
+// of an ordered batch is the same kernels on an offset view of the (hypothesis index, anchor) entries.
+int mvs_launch_k1(mvs_ctx* ctx, int64_t N, const int32_t* ref, double thr, int wid, uint64_t* vis, double* avg,
+                  int32_t* count, float* ncc, bool sort, int64_t p0, int64_t p1, cudaStream_t s) {
+    if (p1 > N) p1 = N;
+    if (p0 >= p1) return MVS_OK;
+    if (!sort && p0 != 0) {                                // input-order batches are indexed by position: no sub-ranges
+        mvs_set_error("mvs_launch_k1: a position range needs an ordered batch");
+        return MVS_ERR_ARG;
+    }
+    const uint32_t* anchors = ctx->d_bin_anchor;
+    const uint2* entries = sort ? (const uint2*)ctx->d_bin_entry + p0 : nullptr;
+    ScoreArgs A;
+    A.gray4 = ctx->d_gray; A.smap = ctx->d_smap; A.vmap = ctx->d_vmap;
+    A.V = ctx->V; A.Vp = ctx->Vp; A.Q = ctx->Q; A.W = ctx->W;
+    A.gstride = ctx->gstride; A.rowpitch = ctx->rowpitch;
+    A.ref = ref; A.thr = thr; A.vis_out = vis; A.avg_out = avg; A.count_out = count; A.ncc_out = ncc;
+    const int64_t n = p1 - p0;
+    int rc;
+    switch (wid) {
+        case 1: rc = launch_gather<1>(ctx, A, n, anchors, entries, s); break;
+        case 2: rc = launch_gather<2>(ctx, A, n, anchors, entries, s); break;
+        case 3: rc = launch_gather<3>(ctx, A, n, anchors, entries, s); break;
+        case 4: rc = launch_gather<4>(ctx, A, n, anchors, entries, s); break;
+        case 5: rc = launch_gather<5>(ctx, A, n, anchors, entries, s); break;
+        case 6: rc = launch_gather<6>(ctx, A, n, anchors, entries, s); break;
+        default: rc = launch_gather<7>(ctx, A, n, anchors, entries, s); break;
+    }
+    ctx->launches++;
+    MVS_CUDA_CHECK(cudaGetLastError());
+    return rc;
+}
+
 int mvs_launch_score_refexact(mvs_ctx* ctx, int64_t N, const double* c, const int32_t* ref, double thr, int wid,
                               uint64_t* vis, double* avg, int32_t* count, double* xy, float* ncc, cudaStream_t s) {
     if (N == 0) return MVS_OK;
@@ -1114,29 +1162,12 @@ int mvs_launch_score_refexact(mvs_ctx* ctx, int64_t N, const double* c, const in
     if ((rc = mvs_build_window_maps(ctx, wid, s)) != MVS_OK) return rc;
     const bool sort = N >= MVS_SORT_MIN;
     if ((rc = mvs_bin_hypotheses(ctx, N, c, ref, wid, sort, vis, avg, count, xy, ncc, s)) != MVS_OK) return rc;
-    const uint32_t* anchors = ctx->d_bin_anchor;
-    const uint2* entries = sort ? (const uint2*)ctx->d_bin_entry : nullptr;
-    ScoreArgs A;
-    A.gray4 = ctx->d_gray; A.smap = ctx->d_smap; A.vmap = ctx->d_vmap;
-    A.V = ctx->V; A.Vp = ctx->Vp; A.Q = ctx->Q; A.W = ctx->W;
-    A.gstride = ctx->gstride; A.rowpitch = ctx->rowpitch;
-    A.ref = ref; A.thr = thr; A.vis_out = vis; A.avg_out = avg; A.count_out = count; A.ncc_out = ncc;
     const int pslot = (int)(ctx->prof_n % MVS_PROF_RING);
     if (ctx->profile) MVS_CUDA_CHECK(cudaEventRecord(ctx->prof_ev[2 * pslot], s));
-    switch (wid) {
-        case 1: rc = launch_gather<1>(ctx, A, N, anchors, entries, s); break;
-        case 2: rc = launch_gather<2>(ctx, A, N, anchors, entries, s); break;
-        case 3: rc = launch_gather<3>(ctx, A, N, anchors, entries, s); break;
-        case 4: rc = launch_gather<4>(ctx, A, N, anchors, entries, s); break;
-        case 5: rc = launch_gather<5>(ctx, A, N, anchors, entries, s); break;
-        case 6: rc = launch_gather<6>(ctx, A, N, anchors, entries, s); break;
-        default: rc = launch_gather<7>(ctx, A, N, anchors, entries, s); break;
-    }
+    rc = mvs_launch_k1(ctx, N, ref, thr, wid, vis, avg, count, ncc, sort, 0, N, s);
     if (ctx->profile) {
         MVS_CUDA_CHECK(cudaEventRecord(ctx->prof_ev[2 * pslot + 1], s));
         ctx->prof_n++;
     }
-    ctx->launches++;
-    MVS_CUDA_CHECK(cudaGetLastError());
     return rc;
 }

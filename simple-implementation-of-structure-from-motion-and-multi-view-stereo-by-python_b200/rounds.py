@@ -127,12 +127,15 @@ class DeviceBackend:
         return full[:total], counts
 
     # -- the whole expansion in one C call (mvs_expand_run) ---------------------------------------
-    def exchange_setup(self, capacity, world, group):
+    def exchange_setup(self, capacity, world, group, parts=1, parts_min=0):
         """Symmetric-memory inbox (minimal wire, two parity halves) + barrier flags for the fused multi-GPU
-        rounds.  Collective over ``group``.  Raises when symmetric memory / peer access is unavailable."""
+        rounds.  Collective over ``group``.  Raises when symmetric memory / peer access is unavailable.
+        parts > 1 (the same on every rank): shards of at least ``parts_min`` candidates (<= 0: 2^17) are scored in
+        ``parts`` position ranges, the exchange of one range under the scoring of the next (mvs_exchange_set_parts)."""
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
         t = self.torch
+        _check(self.lib.mvs_exchange_set_parts(self.ctx._h, int(parts), int(parts_min)), "mvs_exchange_set_parts")
         nbytes = int(self.lib.mvs_exchange_bytes(self.ctx._h, world, capacity))
         inbox = symm_mem.empty(nbytes, dtype=t.uint8, device=self.device)
         flags = symm_mem.empty(world + 1, dtype=t.int64, device=self.device)     # one flag per peer + this GPU's epoch counter
