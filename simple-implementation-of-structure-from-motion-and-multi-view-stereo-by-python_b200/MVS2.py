@@ -462,9 +462,9 @@ def patch_expansion(args, imgs, initial_patches, cells, camera_pos, visible_lowe
         # otherwise every rank falls back to the stepwise driver with a collective all-gather
         from .rounds import agree_on_fused_exchange
         cap = int(os.environ.get("MVS_ROUND_CAPACITY", str(1 << 21)))
-        # rounds whose shard reaches 2^17 candidates publish in position ranges under the scoring (mvs_exchange_set_parts);
-        # dinoRing's rounds (<= 61 k candidates) stay below it, larger scenes do not
-        parts = int(os.environ.get("MVS_EXCHANGE_PARTS", "2"))
+        # MVS_EXCHANGE_PARTS > 1: rounds whose shard reaches 2^17 candidates publish in position ranges under the scoring
+        # (mvs_exchange_set_parts).  Off by default: measured on 8 GPUs it buys 2 % at best (exchange section)
+        parts = int(os.environ.get("MVS_EXCHANGE_PARTS", "1"))
         ok, why = agree_on_fused_exchange(lambda: be.exchange_setup(cap, world, dist.group.WORLD, parts=parts), dist, be.device)
         if not ok:
             if rank == 0:

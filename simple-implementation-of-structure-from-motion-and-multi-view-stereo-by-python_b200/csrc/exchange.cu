@@ -289,9 +289,12 @@ int mvs_launch_publish(mvs_ctx* ctx, int64_t N, const uint64_t* vis, const doubl
 // enqueued at once and the hardware works through them back to back WITHOUT draining the GPU in between (the CTAs of
 // the next launch fill the slots the previous one frees); the P launches share the grid cap of one launch, so the
 // batch is scored by as many CTAs as before.  The publish of a finished range then runs while the other ranges are
-// still being scored, and only the publish of the range that finishes last is exposed.  Measured on one B200 (2^20
-// hypotheses, nothing to hide there): 0.399 ms per step plain, 0.408 with two ranges, 0.423 with four.  Measured and
-// rejected: the ranges as consecutive launches on ONE stream (every extra launch costs ~40 us of drain and ramp-up:
+// still being scored, and only the publish of the range that finishes last is exposed.  OFF by default
+// (mvs_exchange_set_parts): measured per step of 2^20 hypotheses per GPU, plain / two ranges / four ranges -- 0.399 /
+// 0.408 / 0.423 ms on one GPU (nothing to hide there), 0.512 / 0.517 / 0.532 ms on eight; with MVS_XMODE=1 (descending
+// stream priorities) 0.502 ms on eight.  K1's two CTAs per SM fill the register file, so a publish CTA only runs where
+// a K1 CTA has retired: at equal priority the publish queues behind the next range's CTAs, with priority it fragments
+// the SMs.  Measured and rejected before that: the ranges as consecutive launches on ONE stream (every extra launch costs ~40 us of drain and ramp-up:
 // K1 0.326 -> 0.367 ms for two ranges); ONE K1 launch whose warps report finished chunks into per-range counters for
 // a gate kernel on the side stream (the __threadfence before every report costs as much: 0.326 -> 0.363 ms); side
 // streams of DESCENDING priority (the high-priority publish CTAs fragment the register file K1's two CTAs per SM
