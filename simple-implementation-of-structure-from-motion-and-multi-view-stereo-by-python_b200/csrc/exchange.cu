@@ -244,9 +244,9 @@ static int launch_publish_part(mvs_ctx* ctx, int64_t N, const uint64_t* vis, con
     const int T = (int)((N + XTILE - 1) / XTILE);
     int32_t* tiles = ctx->d_tiles + (size_t)part_id * (T + 1);          // (sized by the caller for all parts)
     unsigned* ticket = (unsigned*)ctx->d_ticket + part_id;
-    // a publish that shares the GPU with K1 (the side stream of the overlapped exchange) runs as a FEW persistent CTAs:
-    // K1's two CTAs per SM hold the whole register file, so every SM a publish CTA lands on scores at half occupancy
-    // meanwhile; NVLink-rate stores need only a few SMs
+    // one CTA per tile.  (max_ctas > 0 caps the grid -- the kernels walk the tiles with a grid stride -- for a publish that
+    // shares the GPU with K1; measured with 16 .. 128 CTAs the publish itself became the long pole (0.93 .. 0.48 ms per
+    // step against 0.40), so no caller uses it)
     int grid = T > 0 ? T : 1;                              // T == 0: an empty shard
     if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
     publish_count_scan<<<grid, 256, 0, s>>>(count, gate, bound, N, tiles, T, P, ticket, S);
@@ -294,8 +294,8 @@ int mvs_launch_publish(mvs_ctx* ctx, int64_t N, const uint64_t* vis, const doubl
 // 0.408 / 0.423 ms on one GPU (nothing to hide there), 0.512 / 0.517 / 0.532 ms on eight; with MVS_XMODE=1 (descending
 // stream priorities) 0.502 ms on eight.  K1's two CTAs per SM fill the register file, so a publish CTA only runs where
 // a K1 CTA has retired: at equal priority the publish queues behind the next range's CTAs, with priority it fragments
-// the SMs.  Measured and rejected before that: the ranges as consecutive launches on ONE stream (every extra launch costs ~40 us of drain and ramp-up:
-// K1 0.326 -> 0.367 ms for two ranges); ONE K1 launch whose warps report finished chunks into per-range counters for
+// the SMs.  Measured and rejected before that: the ranges as consecutive launches on ONE stream
+// (every extra launch costs ~40 us of drain and ramp-up: K1 0.326 -> 0.367 ms for two ranges); ONE K1 launch whose warps report finished chunks into per-range counters for
 // a gate kernel on the side stream (the __threadfence before every report costs as much: 0.326 -> 0.363 ms); side
 // streams of DESCENDING priority (the high-priority publish CTAs fragment the register file K1's two CTAs per SM
 // fill completely: 0.420 vs 0.408 ms); range launches of one chunk per CTA (0.438 ms: 1.7 chunks per CTA through the
@@ -350,8 +350,10 @@ int mvs_launch_score_publish(mvs_ctx* ctx, int64_t N, const double* c, const int
             return rc;
         }
         if ((rc = launch_publish_part(ctx, N, vis, avg, count, gate, bound, peer_inbox, rank, world, capacity, parity, k, P,
-                                      ctx->d_bin_part, S, q)) != MVS_OK)
+                                      ctx->d_bin_part, S, q)) != MVS_OK) {
+            ctx->k1_share = 0;
             return rc;
+        }
         MVS_CUDA_CHECK(cudaEventRecord(ctx->x_ev[k], q));
     }
     // ---- the last range on the caller's stream, then join
