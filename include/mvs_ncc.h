@@ -17,7 +17,13 @@
  *     synchronises before returning; device mode only enqueues work on `stream`
  *     (a cudaStream_t passed as void*; NULL = the legacy default stream).
  *   - one context per GPU; calls on one context must be serialised by the caller
- *     (thread-compatible, not thread-safe).
+ *     (thread-compatible, not thread-safe).  Device-mode calls of one context share
+ *     its scratch buffers (ordering scratch, window maps, candidate arrays): enqueue
+ *     them on ONE stream, or order the streams with events -- two streams running
+ *     calls of the same context concurrently is a data race.  A CUDA graph captured
+ *     from such calls replays with the buffer addresses of capture time: run the
+ *     sequence once eagerly first (scratch buffers grow on demand) and re-capture
+ *     after any call that handles a larger batch.
  *   - there is NO CPU fallback: every entry point fails with MVS_ERR_CUDA when no
  *     sm_100 device is usable.
  */
