@@ -2,9 +2,13 @@
 
 Replaces utils.py:249-251 (export2ply), which builds a pandas DataFrame with columns
 x, y, z, red, green, blue from np.hstack((points, colors)) -- all float64 -- and hands it to
-pyntcloud (not installed here).  pyntcloud writes a binary little-endian PLY whose vertex
-properties carry the DataFrame dtypes, i.e. six ``double`` properties; this writer emits the
-same container directly."""
+pyntcloud (not installed here, so the container below is UNVERIFIED against its writer).  pyntcloud
+writes a binary little-endian PLY with one vertex property per DataFrame column and the raw
+records (here six float64 per vertex) behind the header; this writer emits that payload with the
+properties declared as ``double``, which is what the 48-byte records are.  (From memory of
+pyntcloud's io/ply.py -- not checkable here -- its header generator names a property by the first
+letter of the dtype, i.e. ``float`` for float64 too, which would make its own float64 files
+unreadable by standard PLY readers; if so, this writer deliberately does not reproduce that.)"""
 import numpy as np
 
 
