@@ -233,3 +233,44 @@ def test_ref_port_reproduces_the_reference(golden):
     finally:
         pool.close()
     assert [r[0] for r in res] == [int(d["t07_vis"][i].sum()) for i in idx]
+
+
+# ---- the plain-C restatement (oracle/mode_a.c): a second, independent checker pinned to the same golden vectors
+@pytest.mark.parametrize("name", ["dino12_scores", "synth5_scores"])
+@pytest.mark.parametrize("tag,thr", [("t04", 0.4), ("t07", 0.7)])
+@pytest.mark.parametrize("threads", [1, 0])
+def test_c_restatement_matches_reference(golden, name, tag, thr, threads):
+    from oracle import c_port
+    d = golden(name)
+    gray = c_port.gray_from_rgb(d["rgb"])
+    assert (gray == mode_a.gray_from_rgb(d["rgb"])).all()
+    o = c_port.score(gray, _cams(d), d["c"], d["ref"], thr, threads=threads)
+    assert (o["vis"] == d[tag + "_vis"]).all()                       # the reference's own visible sets: exact
+    assert (np.isnan(o["ncc"]) == np.isnan(d[tag + "_ncc"])).all()
+    assert np.nanmax(np.abs(o["ncc"] - d[tag + "_ncc"])) < 1e-12
+    assert np.abs(o["avg"] - d[tag + "_avg"]).max() < 1e-12
+    seen = ~np.isnan(d[tag + "_xy"][:, 0])
+    assert (o["x"][seen] == d[tag + "_xy"][seen, 0]).all()           # projection: bit-exact vs cv2
+    assert (o["y"][seen] == d[tag + "_xy"][seen, 1]).all()
+
+
+def test_c_restatement_equals_numpy_oracle_on_other_windows(golden):
+    """Window half-sizes the reference never uses (it hard-codes 5) and a seeded list that covers every side of the
+    bounds rule: the two restatements, written independently, must agree exactly."""
+    from oracle import c_port
+    d = golden("dino12_scores")
+    cams = _cams(d)
+    gray = mode_a.gray_from_rgb(d["rgb"])
+    rng = np.random.default_rng(11)
+    pick = rng.integers(0, len(d["c"]), 600)
+    c = d["c"][pick] + rng.normal(0, 3e-4, (600, 3))
+    ref = rng.integers(0, gray.shape[0], 600)
+    c[0] = np.nan                                                     # non-finite projection: rejected by both
+    for wid in (1, 3, 5, 7):
+        a = mode_a.score(gray, cams, c, ref, 0.55, wid=wid)
+        b = c_port.score(gray, cams, c, ref, 0.55, wid=wid)
+        assert (a["vis"] == b["vis"]).all() and (a["count"] == b["count"]).all()
+        assert np.array_equal(a["x"], b["x"], equal_nan=True) and np.array_equal(a["y"], b["y"], equal_nan=True)
+        assert (np.isnan(a["ncc"]) == np.isnan(b["ncc"])).all()
+        assert np.nanmax(np.abs(a["ncc"] - b["ncc"])) < 1e-13
+        assert np.abs(a["avg"] - b["avg"]).max() < 1e-13
