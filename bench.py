@@ -206,32 +206,53 @@ class CpuArm:
             self.pool.close()
 
 
-def c_port_rate(wl, rgb, K, R, t, c, ref, target_s=3.0):
-    """Informational second CPU figure: the plain-C restatement oracle/mode_a.c (resident gray stack, exact integer
-    window sums, OpenMP over all cores) -- what a tuned CPU implementation of Mode A reaches, NOT the reference's CPU
-    path (that is CpuArm).  Returns a dict for the JSON line, or None when it cannot be built or run."""
+def run_c_port(args):
+    """--impl c_port (internal, CPU only): the plain-C restatement oracle/mode_a.c on the workload's seeded list, with a
+    resident gray stack and OpenMP over all cores; prints one JSON dict.  Run as a CHILD process by c_port_rate so that
+    its OpenMP runtime never shares a process with torch's."""
+    wl = args.workload
+    from oracle import c_port, mode_a
+    from oracle.cameras import Cameras
+    rgb, K, R, t = make_ring_host(wl)
+    c, _, ref = make_hypotheses(wl, min(args.hyps, 1 << 20), 0)
+    gray = mode_a.gray_from_rgb(rgb)
+    cams = Cameras(K, R, t)
+    wid = WORKLOADS[wl]["wid"]
+    n0 = min(len(c), 4096)
+    c_port.score(gray, cams, c[:n0], ref[:n0], THR, wid=wid, want_ncc=False)              # build + spin up
+    t0 = time.perf_counter()
+    c_port.score(gray, cams, c[:n0], ref[:n0], THR, wid=wid, want_ncc=False)
+    dt0 = max(time.perf_counter() - t0, 1e-5)
+    n = int(min(len(c), max(n0, n0 * 3.0 / dt0)))
+    t0 = time.perf_counter()
+    c_port.score(gray, cams, c[:n], ref[:n], THR, wid=wid, want_ncc=False)
+    dt = time.perf_counter() - t0
+    print(json.dumps({"value": n / dt, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                      "sample": f"first {n} hypotheses of the same seeded list, {dt:.2f} s",
+                      "note": "oracle/mode_a.c: plain-C restatement with a resident gray stack and exact integer window sums, "
+                              "OpenMP over all cores -- a tuned CPU implementation, not the reference's cost structure "
+                              "(informational)"}), flush=True)
+    return 0
+
+
+def c_port_rate(wl):
+    """Informational second CPU figure (cpu_baseline.tuned_c_port): what a tuned CPU implementation of Mode A reaches --
+    NOT the reference's CPU path (that is CpuArm).  Child process, bounded; None when it does not apply, a dict with
+    "unavailable" when it fails: the bench line is never lost over it."""
+    w = WORKLOADS[wl]
+    if w["mode"] != "A" or w["V"] * w["H"] * w["W"] > 64 * 480 * 640:
+        return None
     try:
-        if WORKLOADS[wl]["mode"] != "A":
-            return None
-        from oracle import c_port, mode_a
-        from oracle.cameras import Cameras
-        gray = mode_a.gray_from_rgb(rgb)
-        cams = Cameras(K, R, t)
-        wid = WORKLOADS[wl]["wid"]
-        n0 = min(len(c), 4096)
-        c_port.score(gray, cams, c[:n0], ref[:n0], THR, wid=wid, want_ncc=False)          # build + spin up
-        t0 = time.perf_counter()
-        c_port.score(gray, cams, c[:n0], ref[:n0], THR, wid=wid, want_ncc=False)
-        dt0 = max(time.perf_counter() - t0, 1e-5)
-        n = int(min(len(c), max(n0, n0 * target_s / dt0)))
-        t0 = time.perf_counter()
-        c_port.score(gray, cams, c[:n], ref[:n], THR, wid=wid, want_ncc=False)
-        dt = time.perf_counter() - t0
-        return {"value": n / dt, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
-                "sample": f"first {n} hypotheses of the same seeded list, {dt:.2f} s",
-                "note": "oracle/mode_a.c: plain-C restatement with a resident gray stack and exact integer window sums, OpenMP "
-                        "over all cores -- a tuned CPU implementation, not the reference's cost structure (informational)"}
-    except Exception as e:                                                               # never lose the bench line over it
+        import subprocess
+        env = dict(os.environ)
+        for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+            env.pop(k, None)
+        res = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "c_port", "--workload", wl],
+                             capture_output=True, text=True, timeout=180, env=env)
+        if res.returncode != 0:
+            return {"unavailable": "exit %d: %s" % (res.returncode, res.stderr.strip()[-200:])}
+        return json.loads(res.stdout.strip().splitlines()[-1])
+    except Exception as e:
         return {"unavailable": "%s: %s" % (type(e).__name__, e)}
 
 
@@ -269,7 +290,7 @@ def run_reference(args):
     total = sum(times)
     value = per_step * len(times) / total
     sample = f"{per_step} hypotheses per step of the same seeded workload; {arm.kind_note}"
-    tuned = c_port_rate(wl, rgb, K, R, t, c, ref)
+    tuned = c_port_rate(wl)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
@@ -686,7 +707,7 @@ def run_b200(args):
                 arm.close()
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": arm.cores, "kind": "port",
                                     "sample": f"first {n_sample} hypotheses of the same seeded list, {dt:.1f} s; {arm.kind_note}"}
-            tuned = c_port_rate(wl, rgb_host, K, R, t, c, ref)
+            tuned = c_port_rate(wl)
             if tuned is not None:
                 line["cpu_baseline"]["tuned_c_port"] = tuned
         print(json.dumps(line), flush=True)
@@ -943,12 +964,14 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "c_port"])
     ap.add_argument("--workload", default="dino48", choices=sorted(WORKLOADS) + ["dino_rounds"])
     ap.add_argument("--hyps", type=int, default=1 << 20, help="hypotheses per GPU per round")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-baseline", action="store_true", help="also time the CPU port on the large rings")
     args = ap.parse_args()
+    if args.impl == "c_port":
+        return run_c_port(args)
     if args.workload == "dino_rounds":
         if args.impl == "reference":
             raise SystemExit("--impl reference times the synthetic workloads (dino48 by default); dino_rounds reports its own cpu_baseline")
